@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Headline benchmark: SDC sweep DOF-node updates/s on the configuration BASELINE.json quotes
+(3-D heat 511^3 fp64, generic_implicit, M=4 RADAU-RIGHT nodes, QI='MIN-SR-NS' -> node-batched solves).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --steps 1 --warmup 0         # the reference algorithm on the host cores
+
+One "step" = one SDC time step on a fresh seeded random field: predict + K=4 x (update_nodes + compute_residual) +
+compute_end_point, i.e. N*M*4 DOF-node updates.  Prints ONE JSON line (contract in the task description; field meanings
+in DESIGN.md section "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_NODES, K_SWEEPS = 4, 4
+METRIC = "SDC sweep DOF-node updates/s (3D heat 511^3, M=4 MIN-SR-NS, fp64)"
+UNIT = "DOF-node updates/s"
+
+
+def spec_for(n, K=K_SWEEPS):
+    """Description of the headline workload for an n^3 grid, as a fixture-style spec."""
+    return dict(problem="heatNd_unforced", sweeper="generic_implicit",
+                problem_params=dict(nvars=[n, n, n], nu=0.1, freq=[1, 1, 1], bc="dirichlet-zero", solver_type="CG",
+                                    lintol=1e-12, liniter=10000),
+                sweeper_params=dict(num_nodes=M_NODES, quad_type="RADAU-RIGHT", QI="MIN-SR-NS", initial_guess="spread"),
+                level_params=dict(dt=1e-3, restol=-1.0), step_params=dict(maxiter=K),
+                t0=0.0, Tend=1e-3, u0="random", seed=1234)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle restatement of the reference algorithm (scipy sparse + scipy cg)
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(n, K):
+    """One SDC step of the headline description at n^3 with the oracle port; the sparse operator is assembled outside
+    the timed region (the reference does that in the problem constructor)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sdc_oracle
+
+    spec = spec_for(n, K)
+    t0 = time.perf_counter()
+    L = sdc_oracle.make_level(spec)
+    t_setup = time.perf_counter() - t0
+    u0 = sdc_oracle.initial_value(L.prob, spec)
+    t0 = time.perf_counter()
+    out = sdc_oracle.run_sdc(spec, u0=u0, level=L)
+    secs = time.perf_counter() - t0
+    return dict(rate=n**3 * M_NODES * K / secs, seconds=secs, setup_seconds=t_setup, n=n, K=K,
+                cg_per_solve=out["work"]["CG"][0] / (M_NODES * K))
+
+
+def run_reference(args):
+    n = args.ref_n
+    t_all = time.perf_counter()
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(n, K_SWEEPS)
+    for _ in range(max(args.steps, 1)):
+        rates.append(cpu_reference_rate(n, K_SWEEPS))
+    secs = sum(r["seconds"] for r in rates)
+    value = n**3 * M_NODES * K_SWEEPS * len(rates) / secs
+    sample = (f"oracle port of the reference path (scipy sparse matvec + scipy cg), same description at {n}^3 "
+              f"(bounded sample of the 511^3 workload), {K_SWEEPS} sweeps/step, {rates[0]['cg_per_solve']:.1f} CG it/solve")
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(rates),
+                warmup=args.warmup, ms_per_step=1e3 * secs / len(rates), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=f"heat3d_{n}cubed_M4_MINSRNS_K{K_SWEEPS} (CPU sample of heat3d_511cubed)",
+                            inputs="seeded N(0,1) field, default_rng(1234)"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                wall_s=time.perf_counter() - t_all)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pysdc_b200 import backend as bk
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.problems import heatNd_unforced
+    from pysdc_b200.sweepers import generic_implicit
+
+    be = bk.get_backend()
+    n = args.n
+    spec = spec_for(n)
+    pp = dict(spec["problem_params"])
+    pp["nvars"], pp["freq"] = tuple(pp["nvars"]), tuple(pp["freq"])
+    description = dict(problem_class=heatNd_unforced, problem_params=pp, sweeper_class=generic_implicit,
+                       sweeper_params=dict(spec["sweeper_params"]), level_params=dict(spec["level_params"]),
+                       step_params=dict(spec["step_params"]))
+    ctrl = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40}, description=description)
+    P = ctrl.MS[0].levels[0].prob
+
+    # every rank owns an independent n^3 grid ("weak": fixed work per GPU); seeded field generated on the host
+    rng = np.random.default_rng(1234 + rank)
+    host_u0 = torch.empty((n, n, n), dtype=torch.float64).pin_memory()
+    host_u0.numpy()[...] = rng.standard_normal((n, n, n))
+    host_uend = torch.empty((n, n, n), dtype=torch.float64).pin_memory()
+    u0 = P.dtype_u(P.init)
+    u0.data.copy_(host_u0, non_blocking=True)
+    dof_updates_per_step = n**3 * M_NODES * K_SWEEPS
+
+    def step():
+        return ctrl.run(u0=u0, t0=0.0, Tend=1e-3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    # ---- device-resident timing -------------------------------------------------------------------------------------
+    P.solve_log = []
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = be.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        uend, stats = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = be.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    solve_log, P.solve_log = P.solve_log, None
+
+    # ---- end to end through the public API with host buffers --------------------------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        u0.data.copy_(host_u0, non_blocking=True)           # H2D of the step's input from pinned memory
+        uend, stats = step()
+        host_uend.copy_(uend.data, non_blocking=True)       # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # dominant kernel: the persistent batched CG.  Algorithmic bytes per launch:
+        # sum over the B systems of 8 B * N * (4 [set-up: read b, x0; write r, p] + 9 * iterations)
+        cg_ms = sum(a.elapsed_time(b) for a, b, _ in solve_log)
+        cg_iters = torch.stack([c for _, _, c in solve_log]).cpu().numpy().astype(np.int64)
+        alg_bytes = 8.0 * n**3 * float(np.sum(4 + 9 * cg_iters))
+        n_launch = len(solve_log)
+        achieved = alg_bytes / (cg_ms * 1e-3) / 1e9
+        n_cg = float(cg_iters.mean())
+        value = world * dof_updates_per_step * args.steps / (ms * 1e-3)
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f64", data="synthetic",
+                    config=dict(workload=f"heat3d_{n}cubed_M4_MINSRNS_K{K_SWEEPS}", parallelism=f"replicas x{world}" if world > 1 else "single GPU",
+                                cache="working set per step ~28 GB >> 126 MB L2: no flush needed",
+                                inputs="seeded N(0,1) field, default_rng(1234+rank)", cg_it_per_solve=n_cg,
+                                b_alg_bytes_per_update=84 + 72 * n_cg),
+                    e2e=dict(value=world * dof_updates_per_step * args.steps / (ms_e2e * 1e-3), unit=UNIT,
+                             h2d_bytes_per_step=8 * n**3, d2h_bytes_per_step=8 * n**3),
+                    gpu_launches=launches,
+                    roofline=dict(bound="hbm", kernel="cg_kernel<3,false> (persistent batched CG)", achieved=achieved,
+                                  peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src, traffic=None,
+                                  launches=n_launch, ms_per_launch=cg_ms / max(n_launch, 1),
+                                  share_of_step=cg_ms / ms,
+                                  whole_step_achieved=(84 + 72 * n_cg) * dof_updates_per_step * args.steps / (ms * 1e-3) / 1e9),
+                    clocks=clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_rate(args.ref_n, K_SWEEPS)
+            line["cpu_baseline"] = dict(
+                value=r["rate"], unit=UNIT, cores=1, kind="port",
+                sample=(f"oracle port of the reference path (scipy sparse matvec + scipy cg, single-threaded) on this "
+                        f"host, same description at {r['n']}^3, 1 step of {K_SWEEPS} sweeps in {r['seconds']:.1f} s, "
+                        f"{r['cg_per_solve']:.1f} CG it/solve; host has {os.cpu_count()} cores"))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=511, help="grid points per dimension (headline: 511)")
+    ap.add_argument("--ref-n", type=int, default=95, help="grid size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", 0)) == 0:
+            run_reference(args)
+        return
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

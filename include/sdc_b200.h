@@ -1,0 +1,119 @@
+/*
+ * sdc_b200.h — C ABI of libsdcb200.so: the sm_100a kernels behind pySDC's SDC sweep hot path.
+ *
+ * Boundary.  The reference (pySDC, pure Python) has no FFI: its "plugin API" is a set of Python classes chosen
+ * through the `description` dict (pySDC/core/step.py:109-160, pySDC/core/level.py:61-88).  The Python classes in
+ * `pysdc_b200/` mirror those classes one-to-one and call THIS library through ctypes; each entry point below names
+ * the reference code it replaces (paths relative to /root/reference/pySDC).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer named *_dev / every `double*` field argument is a DEVICE pointer to fp64 data in the padded
+ *     layout described below; `const double* const*` arguments are HOST arrays of such device pointers;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is asynchronous on it;
+ *   - every function returns 0 on success, non-zero on failure; sdcb200_last_error() describes the last failure
+ *     of the calling thread.  Nothing falls back to the CPU.
+ *
+ * Field layout ("walled" layout).  A field on an n^ndim grid is stored with pitch P = n + (n & 1) in every
+ * dimension, i.e. volume V = P^ndim doubles, row-major (x fastest), preceded by a guard of G zero doubles
+ * (G = P^(ndim-1) rounded up to a multiple of 16).  Field pointers passed to this library point at element
+ * (0,..,0), i.e. just after the guard.
+ *   - Dirichlet-zero grids have odd n (the reference enforces it: generic_ND_FD.py:127-131), so P = n+1 and the
+ *     extra index in every dimension is a zero "wall": it IS the homogeneous boundary value, and the wall/guard
+ *     make every 3/5/7-point neighbour access in-bounds and branch-free.  Kernels never write non-zero walls.
+ *   - periodic grids have even n, so P = n (dense); neighbours wrap explicitly.
+ *   Several fields of one batch may live anywhere; kernels take pointer arrays, not a stacked tensor.
+ */
+#ifndef SDC_B200_H
+#define SDC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDCB200_MAX_NODES 8   /* max collocation nodes / batched systems per launch */
+#define SDCB200_MAX_TERMS 24  /* max input fields of one collocation launch ((M+1) * components) */
+
+#define SDCB200_BC_DIRICHLET 0
+#define SDCB200_BC_PERIODIC 1
+
+int sdcb200_version(void);
+const char* sdcb200_last_error(void);
+/* SM count, compute capability and co-resident CTA capacity of the persistent solver kernel on the current device */
+int sdcb200_device_info(int* sm_count, int* cc_major, int* cc_minor, int* solver_ctas);
+
+/* ---- layout helpers (host only) -------------------------------------------------------------------------------- */
+long long sdcb200_pitch(int n);
+long long sdcb200_volume(int ndim, int n);
+long long sdcb200_guard(int ndim, int n);
+
+/* ---- K6: datatype utilities (datatype_classes/mesh.py) --------------------------------------------------------- */
+/* max |x_i| over `count` doubles -> *out_dev (device double).  Replaces mesh.__abs__ (mesh.py:65-83). */
+int sdcb200_maxabs(const double* x, long long count, double* out_dev, void* stream);
+/* out = a*x + b*y (y may be NULL -> out = a*x).  Plain streaming helper for the datatype operators (mesh.py:51-63) */
+int sdcb200_axpby(long long count, double a, const double* x, double b, const double* y, double* out, void* stream);
+
+/* ---- K1: collocation --------------------------------------------------------------------------------------------
+ * out[m] = (base ? base : 0) + sum_k W[m*nin + k] * in[k] + (add && add[m] ? add[m] : 0),   m < nout, k < nin
+ * One coalesced, double2-vectorised pass: every input is read once, every output written once.
+ * Replaces the M^2 axpy loops of generic_implicit.integrate (generic_implicit.py:29-49), the "known terms" loop of
+ * update_nodes (generic_implicit.py:70-82, imex_1st_order.py:77-88: W = dt*(Q - QI) [and dt*(Q - QE)]), the new-node
+ * rhs additions (generic_implicit.py:87-89) and compute_end_point (generic_implicit.py:123-129).                   */
+int sdcb200_colloc_apply(long long count, int nout, int nin, const double* W_host,
+                         const double* const* in, const double* base, const double* const* add,
+                         double* const* out, void* stream);
+
+/* res[m] = sum_k W[m*nin+k]*in[k] + (u0 - u[m]) + tau[m];  resnorm_dev[m] = max|res[m]|  (device, M doubles).
+ * res_out may be NULL (norm only, nothing written) or an array of M device pointers.
+ * Replaces Sweeper.compute_residual (core/sweeper.py:164-215) incl. the max-norm of mesh.__abs__.                 */
+int sdcb200_colloc_residual(long long count, int M, int nin, const double* W_host,
+                            const double* const* in, const double* u0, const double* const* u,
+                            const double* const* tau, double* const* res_out, double* resnorm_dev, void* stream);
+
+/* ---- K2: right-hand sides ------------------------------------------------------------------------------------------
+ * f = A u with A = a_off * (sum of 2*ndim neighbours) + a_diag * u  (order-2 centred FD Laplacian times nu;
+ * GenericNDimFinDiff.eval_f, generic_ND_FD.py:188-206; matrix entries as built by problem_helper.py:224-241).
+ * B independent fields per launch.  If profile != NULL also writes f_expl[b] = profile * gt[b]
+ * (heatNd_forced.eval_f, HeatEquation_ND_FD.py:162-204: forcing = spatial profile x scalar g(t)).                    */
+int sdcb200_heat_eval_f(int ndim, int n, int bc, double a_diag, double a_off, int B,
+                        const double* const* u, double* const* f_impl,
+                        const double* profile, const double* gt_host, double* const* f_expl, void* stream);
+
+/* f = A u + inv_eps2 * u * (1 - u^nu_exp)   (allencahn_fullyimplicit.eval_f, AllenCahn_2D_FD.py:207-228) */
+int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
+                             const double* const* u, double* const* f, void* stream);
+
+/* ---- K3: node solves ------------------------------------------------------------------------------------------------
+ * Solve (I - factor_b * A) x_b = rhs_b for b < B with unpreconditioned CG following scipy.sparse.linalg.cg
+ * (scipy 1.18: atol' = rtol*||b||, test ||r|| < atol' before each iteration, x0 = incoming x_b), all iterations of
+ * all B systems inside ONE persistent cooperative launch (device-side reductions, grid barriers, per-system
+ * convergence).  Replaces GenericNDimFinDiff.solve_system with solver_type='CG' (generic_ND_FD.py:252-260).
+ * m_diag[b] = 1 - factor_b*a_diag, m_off[b] = -factor_b*a_off (host arrays).  iters_dev[b] += iterations used.
+ * work must hold sdcb200_cg_workspace_bytes() bytes of device memory, 256-byte aligned, ZERO-FILLED by the caller
+ * before its first use and otherwise left alone between calls (the solver keeps the walls of its work fields zero).  */
+size_t sdcb200_cg_workspace_bytes(int ndim, int n, int B);
+int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
+                          const double* const* rhs, double* const* x, double rtol, int maxiter,
+                          void* work, size_t work_bytes, int* iters_dev, void* stream);
+
+/* Direct solve on 1-D grids: (I - factor*A) is a constant-coefficient (cyclic) tridiagonal matrix; Thomas algorithm in
+ * shared memory, one CTA per system (3 <= n <= 8192).  Replaces solver_type='direct' (scipy spsolve,
+ * generic_ND_FD.py:239) for ndim == 1, the reference's CPU tutorial configuration.                                  */
+int sdcb200_heat_direct_solve_1d(int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
+                                 const double* const* rhs, double* const* x, void* stream);
+
+/* ---- K4: Allen-Cahn Newton ------------------------------------------------------------------------------------------
+ * Newton iteration with inner CG on the Jacobian, whole solve in one persistent launch
+ * (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205).  u: in = initial guess, out = solution.
+ * counters_dev[0] += Newton iterations, counters_dev[1] += CG iterations.  inexact_ratio <= 0 disables :176-177.   */
+size_t sdcb200_newton_workspace_bytes(int n);
+int sdcb200_allencahn_newton_solve(int n, double factor, double a_diag, double a_off, double inv_eps2, int nu_exp,
+                                   const double* rhs, double* u, double newton_tol, int newton_maxiter,
+                                   double lin_tol, int lin_maxiter, double inexact_ratio,
+                                   void* work, size_t work_bytes, int* counters_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDC_B200_H */

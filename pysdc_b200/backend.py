@@ -1,0 +1,202 @@
+"""ctypes binding of ``libsdcb200.so`` (C ABI in ``include/sdc_b200.h``) and the ``Backend`` object the host classes use.
+
+PyTorch is plumbing here: device memory (``torch.Tensor`` storage), the current CUDA stream and, for multi-GPU runs,
+``torch.distributed``.  Every numerical operation of the sweep path is a call into the CUDA library; if the library is
+missing or no CUDA device is present the backend raises ``BackendError`` — there is no CPU fallback.
+
+Field arguments are 1-D fp64 tensors viewing the *volume* of a walled field (``layout.Layout``); their ``data_ptr()``
+is element (0,..,0) and the zero guard sits in front of it in the same storage.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from .errors import BackendError
+
+_LIB_NAME = "libsdcb200.so"
+_c_dp = ctypes.c_void_p
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", _LIB_NAME)
+
+
+def _declare(lib):
+    c_int, c_ll, c_d, c_sz = ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_size_t
+    PP = ctypes.POINTER(ctypes.c_void_p)
+    PD = ctypes.POINTER(ctypes.c_double)
+    sig = {
+        "sdcb200_version": (c_int, []),
+        "sdcb200_last_error": (ctypes.c_char_p, []),
+        "sdcb200_device_info": (c_int, [ctypes.POINTER(c_int)] * 4),
+        "sdcb200_pitch": (c_ll, [c_int]),
+        "sdcb200_volume": (c_ll, [c_int, c_int]),
+        "sdcb200_guard": (c_ll, [c_int, c_int]),
+        "sdcb200_maxabs": (c_int, [_c_dp, c_ll, _c_dp, _c_dp]),
+        "sdcb200_axpby": (c_int, [c_ll, c_d, _c_dp, c_d, _c_dp, _c_dp, _c_dp]),
+        "sdcb200_colloc_apply": (c_int, [c_ll, c_int, c_int, PD, PP, _c_dp, PP, PP, _c_dp]),
+        "sdcb200_colloc_residual": (c_int, [c_ll, c_int, c_int, PD, PP, _c_dp, PP, PP, PP, _c_dp, _c_dp]),
+        "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
+        "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
+        "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, _c_dp, c_sz, _c_dp, _c_dp]),
+        "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
+        "sdcb200_newton_workspace_bytes": (c_sz, [c_int]),
+        "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_d, c_d, c_d, c_d, c_int, _c_dp, _c_dp, c_d, c_int, c_d,
+                                                   c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = the .so does not export what include/sdc_b200.h declares
+        fn.restype, fn.argtypes = res, args
+    return sig
+
+
+def load_library(path=None):
+    """Load the shared library and declare every prototype of ``include/sdc_b200.h`` (no GPU needed)."""
+    path = path or lib_path()
+    if not os.path.exists(path):
+        raise BackendError(f"{path} not found: build it with `python -m pysdc_b200.build` "
+                           "(or __graft_entry__.build()); there is no CPU fallback")
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as e:
+        raise BackendError(f"cannot load {path}: {e}") from e
+    lib._sdc_signatures = _declare(lib)
+    return lib
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def _dbl_array(values):
+    values = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    return (ctypes.c_double * values.size)(*values.tolist())
+
+
+class CudaBackend:
+    """Thin, stateless wrapper: torch tensors in, kernel launches on the current torch CUDA stream out."""
+
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise BackendError("no CUDA device visible: pysdc_b200 runs its sweep path on the GPU only")
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.launches = 0  # kernels launched through this backend (bench.py reports it)
+
+    # -- helpers ------------------------------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BackendError(self.lib.sdcb200_last_error().decode())
+
+    def zeros(self, count, dtype=torch.float64):
+        return torch.zeros(count, dtype=dtype, device=self.device)
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def device_info(self):
+        v = [ctypes.c_int(0) for _ in range(4)]
+        self._check(self.lib.sdcb200_device_info(*[ctypes.byref(x) for x in v]))
+        return dict(sm_count=v[0].value, cc=(v[1].value, v[2].value), solver_ctas=v[3].value)
+
+    # -- K6 -----------------------------------------------------------------------------------------------------------
+    def maxabs_async(self, x, out):
+        self.launches += 1
+        self._check(self.lib.sdcb200_maxabs(x.data_ptr(), x.numel(), out.data_ptr(), self._stream()))
+
+    def maxabs(self, x):
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        self.maxabs_async(x, out)
+        return float(out.item())
+
+    def axpby(self, a, x, b, y, out):
+        self.launches += 1
+        self._check(self.lib.sdcb200_axpby(x.numel(), float(a), x.data_ptr(), float(b),
+                                           None if y is None else y.data_ptr(), out.data_ptr(), self._stream()))
+
+    # -- K1 -----------------------------------------------------------------------------------------------------------
+    def colloc_apply(self, W, ins, base, adds, outs):
+        W = np.asarray(W, dtype=np.float64).reshape(len(outs), len(ins))
+        self.launches += 1
+        self._check(self.lib.sdcb200_colloc_apply(
+            outs[0].numel(), len(outs), len(ins), _dbl_array(W), _ptr_array(ins),
+            None if base is None else base.data_ptr(), None if adds is None else _ptr_array(adds),
+            _ptr_array(outs), self._stream()))
+
+    def colloc_residual(self, W, ins, u0, us, taus, res_outs, resnorm):
+        W = np.asarray(W, dtype=np.float64).reshape(len(us), len(ins))
+        self.launches += 1
+        self._check(self.lib.sdcb200_colloc_residual(
+            u0.numel(), len(us), len(ins), _dbl_array(W), _ptr_array(ins), u0.data_ptr(), _ptr_array(us),
+            None if taus is None else _ptr_array(taus), None if res_outs is None else _ptr_array(res_outs),
+            resnorm.data_ptr(), self._stream()))
+
+    # -- K2 -----------------------------------------------------------------------------------------------------------
+    def heat_eval_f(self, lay, bc, a_diag, a_off, us, fs, profile=None, gts=None, fexpls=None):
+        self.launches += 1
+        self._check(self.lib.sdcb200_heat_eval_f(
+            lay.ndim, lay.n, bc, a_diag, a_off, len(us), _ptr_array(us), _ptr_array(fs),
+            None if profile is None else profile.data_ptr(), None if gts is None else _dbl_array(gts),
+            None if fexpls is None else _ptr_array(fexpls), self._stream()))
+
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs):
+        self.launches += 1
+        self._check(self.lib.sdcb200_allencahn_eval_f(lay.n, a_diag, a_off, inv_eps2, int(nu_exp), len(us),
+                                                      _ptr_array(us), _ptr_array(fs), self._stream()))
+
+    # -- K3 / K4 ------------------------------------------------------------------------------------------------------
+    def cg_workspace(self, lay, B):
+        nbytes = self.lib.sdcb200_cg_workspace_bytes(lay.ndim, lay.n, B)
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+        self.launches += 1
+        self._check(self.lib.sdcb200_heat_cg_solve(
+            lay.ndim, lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs), _ptr_array(xs),
+            float(rtol), int(maxiter), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
+
+    def heat_direct_solve_1d(self, lay, bc, m_diag, m_off, rhs, xs):
+        self.launches += 1
+        self._check(self.lib.sdcb200_heat_direct_solve_1d(lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off),
+                                                          _ptr_array(rhs), _ptr_array(xs), self._stream()))
+
+    def newton_workspace(self, lay):
+        nbytes = self.lib.sdcb200_newton_workspace_bytes(lay.n)
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def allencahn_newton_solve(self, lay, factor, a_diag, a_off, inv_eps2, nu_exp, rhs, u, newton_tol, newton_maxiter,
+                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
+        self.launches += 1
+        self._check(self.lib.sdcb200_allencahn_newton_solve(
+            lay.n, float(factor), a_diag, a_off, inv_eps2, int(nu_exp), rhs.data_ptr(), u.data_ptr(),
+            float(newton_tol), int(newton_maxiter), float(lin_tol), int(lin_maxiter),
+            float(inexact_ratio or 0.0), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(), self._stream()))
+
+
+_backend = None
+
+
+def get_backend():
+    """The process-wide backend (created on first use; raises ``BackendError`` without library or GPU)."""
+    global _backend
+    if _backend is None:
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend(backend):
+    """Install a backend object (used by the CPU tests to drive the host logic with a numpy stand-in)."""
+    global _backend
+    _backend = backend
+    return backend

@@ -1,0 +1,522 @@
+// K3: batched conjugate gradients for (I - factor*A) x = b, and K4: the Allen-Cahn Newton solver around it.
+//
+// One persistent cooperative launch runs the WHOLE solve: all CG iterations of all B node systems, the dot-product
+// reductions (warp shuffle -> block -> fixed-order grid reduction, bitwise identical in every CTA so that control
+// flow stays uniform), the per-system convergence tests and the iteration counters live on the device; the host
+// never synchronises inside a solve.  Grid = (co-resident CTAs per SM) x (SM count), software grid barrier
+// (release/acquire at gpu scope).  The recurrence follows scipy.sparse.linalg.cg (scipy 1.18.1, _isolve/iterative.py)
+// statement by statement, including the unfused rounding of  p*=beta; p+=r;  x+=alpha*p;  r-=alpha*q.
+#include "stencil.cuh"
+
+namespace sdcb200 {
+namespace {
+
+struct Sys {
+    const double* b;     // right-hand side
+    double* x;           // in: initial guess, out: solution
+    double* r;
+    double* p;
+    double* q;
+    const double* dvec;  // optional full diagonal of the operator (Allen-Cahn Jacobian); NULL -> m_diag
+    double m_diag;       // 1 - factor*a_diag
+    double m_off;        // -factor*a_off
+};
+
+struct CgArgs {
+    Geom g;
+    int B;
+    Sys s[SDCB200_MAX_NODES];
+    double rtol;
+    int maxiter;
+    double* partials;  // [2][MAX_NODES][gridDim.x]
+    unsigned* bar;     // grid barrier word (zero before the launch)
+    int* iters_out;    // [B], += iterations
+};
+
+struct NewtonArgs {
+    Geom g;
+    double factor, a_diag, a_off, inv_eps2;
+    int nu_exp;
+    const double* rhs;
+    double* u;
+    double* gvec;  // Newton residual
+    double* z;     // Newton update (CG solution)
+    double* dvec;  // Jacobian diagonal
+    double* r;
+    double* p;
+    double* q;
+    double newton_tol, lin_tol, inexact_ratio;
+    int newton_maxiter, lin_maxiter;
+    double* partials;
+    unsigned* bar;
+    int* counters_out;  // [0] += newton iterations, [1] += CG iterations
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// grid-wide barrier (all CTAs co-resident: cooperative launch).  Same protocol as cooperative groups' grid sync:
+// CTA barrier, one thread arrives with a gpu-scope release and spins with gpu-scope acquire, CTA barrier.  CTA 0 adds
+// the complement so that the top bit flips once per generation and the word never needs resetting.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned add = (blockIdx.x == 0) ? (0x80000000u - (gridDim.x - 1)) : 1u;
+        unsigned old;
+        asm volatile("atom.add.release.gpu.u32 %0,[%1],%2;" : "=r"(old) : "l"(bar), "r"(add) : "memory");
+        unsigned cur;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0,[%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while (((old ^ cur) & 0x80000000u) == 0);
+    }
+    __syncthreads();
+}
+
+// Sum the per-CTA partials of one quantity in a fixed order; identical bits in every thread of every CTA.
+__device__ __forceinline__ double grid_sum(const double* partials, int slot, int b, double* scratch) {
+    const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(src + i);
+    return block_sum(v, scratch);
+}
+__device__ __forceinline__ double grid_max(const double* partials, int slot, int b, double* scratch) {
+    const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
+    double v = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v = fmax(v, __ldcg(src + i));
+    return block_max(v, scratch);
+}
+__device__ __forceinline__ void put_partial(double* partials, int slot, int b, double v) {
+    if (threadIdx.x == 0) partials[(size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x + blockIdx.x] = v;
+}
+
+// scalar state of the solver, one copy per CTA in shared memory, written by thread 0 only
+struct CgShared {
+    double scratch[33];
+    double bb[SDCB200_MAX_NODES], rr[SDCB200_MAX_NODES], rho_prev[SDCB200_MAX_NODES];
+    double alpha[SDCB200_MAX_NODES], beta[SDCB200_MAX_NODES];
+    int iters[SDCB200_MAX_NODES];
+    unsigned active;  // bit b set: system b still iterating
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the collective CG routine: every thread of the grid calls it with identical arguments
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NDIM, bool PER>
+__device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, int maxiter, double* partials,
+                              unsigned* bar, CgShared& sh) {
+    const Units U = make_units(g);
+    const long long n2 = g.vol / 2;
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kThreads;
+
+    // ---- r = b - M x0, ||b||^2, ||r||^2 ------------------------------------------------------------------------------
+    for (int b = 0; b < B; ++b) {
+        const Sys& S = s[b];
+        double bb = 0.0, rr = 0.0;
+        for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+            stencil_unit<NDIM, PER>(g, U, S.x, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                const double2 rhs = ld2(S.b + idx);
+                double2 d = make_double2(S.m_diag, S.m_diag);
+                if (S.dvec != nullptr) d = ld2(S.dvec + idx);
+                double2 r;
+                r.x = v0 ? rhs.x - fma(S.m_off, nb.x, d.x * c.x) : 0.0;
+                r.y = v1 ? rhs.y - fma(S.m_off, nb.y, d.y * c.y) : 0.0;
+                st2(S.r + idx, r);
+                if (v0) bb = fma(rhs.x, rhs.x, bb);
+                if (v1) bb = fma(rhs.y, rhs.y, bb);
+                rr = fma(r.x, r.x, rr);
+                rr = fma(r.y, r.y, rr);
+            });
+        }
+        bb = block_sum(bb, sh.scratch);
+        rr = block_sum(rr, sh.scratch);
+        put_partial(partials, 0, b, bb);
+        put_partial(partials, 1, b, rr);
+    }
+    grid_barrier(bar);
+    for (int b = 0; b < B; ++b) {
+        const double bb = grid_sum(partials, 0, b, sh.scratch);
+        const double rr = grid_sum(partials, 1, b, sh.scratch);
+        if (threadIdx.x == 0) {
+            sh.bb[b] = bb;
+            sh.rr[b] = rr;
+            sh.iters[b] = 0;
+            sh.rho_prev[b] = 1.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned act = 0;
+        for (int b = 0; b < B; ++b)
+            if (sh.bb[b] != 0.0) act |= 1u << b;  // scipy: ||b|| == 0 -> return b
+        sh.active = act;
+    }
+    __syncthreads();
+    // systems with a zero right-hand side: solution is b itself (all zeros)
+    for (int b = 0; b < B; ++b) {
+        if (sh.bb[b] == 0.0) {
+            for (long long i = gtid; i < n2; i += gstride) st2(s[b].x + 2 * i, make_double2(0.0, 0.0));
+        }
+    }
+
+    for (int it = 0;; ++it) {
+        // ---- convergence test first (scipy: "if norm(r) < atol: return"), then the iteration budget ----------------
+        if (threadIdx.x == 0) {
+            unsigned act = sh.active;
+            for (int b = 0; b < B; ++b) {
+                if (!(act >> b & 1u)) continue;
+                const double atol = rtol * sqrt(sh.bb[b]);
+                if (sqrt(sh.rr[b]) < atol || it >= maxiter) {
+                    act &= ~(1u << b);
+                } else {
+                    sh.beta[b] = it > 0 ? sh.rr[b] / sh.rho_prev[b] : 0.0;
+                }
+            }
+            sh.active = act;
+        }
+        __syncthreads();
+        const unsigned act = sh.active;
+        if (act == 0) break;
+
+        // ---- p = r + beta p ---------------------------------------------------------------------------------------------
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const Sys& S = s[b];
+            const double beta = sh.beta[b];
+            if (it == 0) {
+                for (long long i = gtid; i < n2; i += gstride) st2(S.p + 2 * i, ld2(S.r + 2 * i));
+            } else {
+                for (long long i = gtid; i < n2; i += gstride) {
+                    const double2 r = ld2(S.r + 2 * i);
+                    double2 p = ld2(S.p + 2 * i);
+                    p.x = __dadd_rn(__dmul_rn(p.x, beta), r.x);
+                    p.y = __dadd_rn(__dmul_rn(p.y, beta), r.y);
+                    st2(S.p + 2 * i, p);
+                }
+            }
+        }
+        grid_barrier(bar);
+
+        // ---- q = M p, p.q -----------------------------------------------------------------------------------------------
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const Sys& S = s[b];
+            double pq = 0.0;
+            for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+                stencil_unit<NDIM, PER>(g, U, S.p, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                    double2 d = make_double2(S.m_diag, S.m_diag);
+                    if (S.dvec != nullptr) d = ld2(S.dvec + idx);
+                    double2 q;
+                    q.x = v0 ? fma(S.m_off, nb.x, d.x * c.x) : 0.0;
+                    q.y = v1 ? fma(S.m_off, nb.y, d.y * c.y) : 0.0;
+                    st2(S.q + idx, q);
+                    pq = fma(c.x, q.x, pq);
+                    pq = fma(c.y, q.y, pq);
+                });
+            }
+            pq = block_sum(pq, sh.scratch);
+            put_partial(partials, 0, b, pq);
+        }
+        grid_barrier(bar);
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const double pq = grid_sum(partials, 0, b, sh.scratch);
+            if (threadIdx.x == 0) sh.alpha[b] = sh.rr[b] / pq;
+        }
+        __syncthreads();
+
+        // ---- x += alpha p, r -= alpha q, r.r ----------------------------------------------------------------------------
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const Sys& S = s[b];
+            const double alpha = sh.alpha[b];
+            double rr = 0.0;
+            for (long long i = gtid; i < n2; i += gstride) {
+                const double2 p = ld2(S.p + 2 * i), q = ld2(S.q + 2 * i);
+                double2 x = ld2(S.x + 2 * i), r = ld2(S.r + 2 * i);
+                x.x = __dadd_rn(x.x, __dmul_rn(alpha, p.x));
+                x.y = __dadd_rn(x.y, __dmul_rn(alpha, p.y));
+                r.x = __dsub_rn(r.x, __dmul_rn(alpha, q.x));
+                r.y = __dsub_rn(r.y, __dmul_rn(alpha, q.y));
+                st2(S.x + 2 * i, x);
+                st2(S.r + 2 * i, r);
+                rr = fma(r.x, r.x, rr);
+                rr = fma(r.y, r.y, rr);
+            }
+            rr = block_sum(rr, sh.scratch);
+            put_partial(partials, 1, b, rr);
+        }
+        grid_barrier(bar);
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const double rr = grid_sum(partials, 1, b, sh.scratch);
+            if (threadIdx.x == 0) {
+                sh.rho_prev[b] = sh.rr[b];
+                sh.rr[b] = rr;
+                sh.iters[b] += 1;  // scipy calls the callback once per completed iteration
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int NDIM, bool PER>
+__global__ void __launch_bounds__(kThreads) cg_kernel(const __grid_constant__ CgArgs a) {
+    __shared__ CgShared sh;
+    cg_collective<NDIM, PER>(a.g, a.B, a.s, a.rtol, a.maxiter, a.partials, a.bar, sh);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.iters_out != nullptr)
+        for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
+}
+
+// u^k for small integer k the way numpy evaluates `u**nu` for nu = 2 (a multiplication); general k by repeated
+// multiplication.
+__device__ __forceinline__ double ipow(double u, int k) {
+    double r = u;
+    for (int i = 1; i < k; ++i) r = __dmul_rn(r, u);
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) newton_kernel(const __grid_constant__ NewtonArgs a) {
+    __shared__ CgShared sh;
+    __shared__ Sys sys;
+    __shared__ int s_newton, s_linear;
+    const Geom& g = a.g;
+    const Units U = make_units(g);
+    const long long n2 = g.vol / 2;
+    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * kThreads;
+    if (threadIdx.x == 0) {
+        s_newton = 0;
+        s_linear = 0;
+        sys.b = a.gvec;
+        sys.x = a.z;
+        sys.r = a.r;
+        sys.p = a.p;
+        sys.q = a.q;
+        sys.dvec = a.dvec;
+        sys.m_diag = 0.0;
+        sys.m_off = -(a.factor * a.a_off);
+    }
+    __syncthreads();
+    double lin_tol = a.lin_tol;
+    int n = 0;
+    while (n < a.newton_maxiter) {
+        // g = u - factor*(A u + 1/eps^2 u (1 - u^nu)) - rhs ;  Jacobian diagonal ;  z = 0  (AllenCahn_2D_FD.py:170,183)
+        double gmax = 0.0;
+        for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+            stencil_unit<2, true>(g, U, a.u, unit, [&](long long idx, double2 c, double2 nb, bool, bool) {
+                const double2 rhs = ld2(a.rhs + idx);
+                double2 gv, dv;
+                {
+                    const double Au = fma(a.a_off, nb.x, a.a_diag * c.x);
+                    const double un = ipow(c.x, a.nu_exp);
+                    const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.x), __dsub_rn(1.0, un));
+                    gv.x = __dsub_rn(__dsub_rn(c.x, __dmul_rn(a.factor, __dadd_rn(Au, react))), rhs.x);
+                    const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
+                    dv.x = __dsub_rn(1.0, __dmul_rn(a.factor, __dadd_rn(a.a_diag, jr)));
+                }
+                {
+                    const double Au = fma(a.a_off, nb.y, a.a_diag * c.y);
+                    const double un = ipow(c.y, a.nu_exp);
+                    const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.y), __dsub_rn(1.0, un));
+                    gv.y = __dsub_rn(__dsub_rn(c.y, __dmul_rn(a.factor, __dadd_rn(Au, react))), rhs.y);
+                    const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
+                    dv.y = __dsub_rn(1.0, __dmul_rn(a.factor, __dadd_rn(a.a_diag, jr)));
+                }
+                st2(a.gvec + idx, gv);
+                st2(a.dvec + idx, dv);
+                st2(a.z + idx, make_double2(0.0, 0.0));
+                gmax = fmax(gmax, fmax(fabs(gv.x), fabs(gv.y)));
+                if (gv.x != gv.x || gv.y != gv.y) gmax = INFINITY;  // NaN: never "converged"
+            });
+        }
+        gmax = block_max(gmax, sh.scratch);
+        put_partial(a.partials, 0, 0, gmax);
+        grid_barrier(a.bar);
+        const double res = grid_max(a.partials, 0, 0, sh.scratch);
+        if (a.inexact_ratio > 0.0) lin_tol = res * a.inexact_ratio;
+        if (res < a.newton_tol) break;
+        grid_barrier(a.bar);  // everybody has read partials slot 0 before the CG reuses it
+
+        cg_collective<2, true>(g, 1, &sys, lin_tol, a.lin_maxiter, a.partials, a.bar, sh);
+        if (threadIdx.x == 0) {
+            s_linear += sh.iters[0];
+            s_newton += 1;
+        }
+        // u -= z
+        for (long long i = gtid; i < n2; i += gstride) {
+            double2 u = ld2(a.u + 2 * i);
+            const double2 z = ld2(a.z + 2 * i);
+            u.x = __dsub_rn(u.x, z.x);
+            u.y = __dsub_rn(u.y, z.y);
+            st2(a.u + 2 * i, u);
+        }
+        grid_barrier(a.bar);
+        ++n;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters_out != nullptr) {
+        a.counters_out[0] += s_newton;
+        a.counters_out[1] += s_linear;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+template <class K>
+int coresident_ctas(K kernel, int* out) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (e != cudaSuccess) return fail_cuda("coresident_ctas", e);
+    if (per_sm < 1) return fail("coresident_ctas", "solver kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;  // 1024 threads/SM already saturate HBM; more CTAs only lengthen the barriers
+    *out = per_sm * sm_count();
+    return 0;
+}
+
+constexpr int kMaxGrid = 148 * 8;  // upper bound used to size the partials area
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WorkLayout {
+    size_t field;          // bytes of one guarded field
+    size_t guard_bytes;
+    size_t partials_off, bar_off, fields_off, total;
+};
+WorkLayout work_layout(int ndim, int n, int nfields) {
+    WorkLayout w;
+    const size_t guard = (size_t)sdcb200_guard(ndim, n), vol = (size_t)sdcb200_volume(ndim, n);
+    w.guard_bytes = guard * sizeof(double);
+    w.field = align_up((guard + vol) * sizeof(double), 256);
+    w.partials_off = 0;
+    w.bar_off = align_up(2 * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
+    w.fields_off = w.bar_off + 256;
+    w.total = w.fields_off + (size_t)nfields * w.field;
+    return w;
+}
+
+template <int NDIM, bool PER>
+int launch_cg(CgArgs& a, cudaStream_t s) {
+    int grid = 0;
+    if (int rc = coresident_ctas(cg_kernel<NDIM, PER>, &grid)) return rc;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    void* params[] = {&a};
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_kernel<NDIM, PER>, dim3(grid), dim3(kThreads), params, 0, s));
+    return 0;
+}
+
+}  // namespace
+}  // namespace sdcb200
+
+using namespace sdcb200;
+
+extern "C" {
+
+int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas) {
+    int dev = 0;
+    SDC_CUDA_OK(cudaGetDevice(&dev));
+    if (sm) SDC_CUDA_OK(cudaDeviceGetAttribute(sm, cudaDevAttrMultiProcessorCount, dev));
+    if (cc_major) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (solver_ctas) {
+        if (int rc = coresident_ctas(cg_kernel<3, false>, solver_ctas)) return rc;
+    }
+    return 0;
+}
+
+size_t sdcb200_cg_workspace_bytes(int ndim, int n, int B) { return work_layout(ndim, n, 3 * B).total; }
+
+int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
+                          const double* const* rhs, double* const* x, double rtol, int maxiter, void* work,
+                          size_t work_bytes, int* iters_dev, void* stream) {
+    SDC_REQUIRE(ndim >= 1 && ndim <= 3, "ndim must be 1, 2 or 3");
+    SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES, "B out of range");
+    SDC_REQUIRE(n >= 2, "grid too small");
+    SDC_REQUIRE(bc == SDCB200_BC_PERIODIC || (n & 1), "dirichlet-zero grids need an odd number of points per dimension");
+    SDC_REQUIRE(bc != SDCB200_BC_PERIODIC || !(n & 1), "periodic grids need an even number of points per dimension");
+    const WorkLayout w = work_layout(ndim, n, 3 * B);
+    SDC_REQUIRE(work != nullptr && work_bytes >= w.total, "workspace too small (see sdcb200_cg_workspace_bytes)");
+    SDC_REQUIRE((reinterpret_cast<size_t>(work) & 255u) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = make_geom(ndim, n, bc);
+    a.B = B;
+    a.rtol = rtol;
+    a.maxiter = maxiter;
+    char* base = static_cast<char*>(work);
+    a.partials = reinterpret_cast<double*>(base + w.partials_off);
+    a.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
+    a.iters_out = iters_dev;
+    for (int b = 0; b < B; ++b) {
+        SDC_REQUIRE(rhs[b] && x[b] && !(reinterpret_cast<size_t>(rhs[b]) & 15u) && !(reinterpret_cast<size_t>(x[b]) & 15u),
+                    "rhs / x missing or misaligned");
+        Sys& S = a.s[b];
+        S.b = rhs[b];
+        S.x = x[b];
+        char* f = base + w.fields_off + (size_t)(3 * b) * w.field;
+        S.r = reinterpret_cast<double*>(f + w.guard_bytes);
+        S.p = reinterpret_cast<double*>(f + w.field + w.guard_bytes);
+        S.q = reinterpret_cast<double*>(f + 2 * w.field + w.guard_bytes);
+        S.dvec = nullptr;
+        S.m_diag = m_diag_host[b];
+        S.m_off = m_off_host[b];
+    }
+    SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    int rc = 1;
+    const bool per = a.g.periodic;
+    if (ndim == 1) rc = per ? launch_cg<1, true>(a, s) : launch_cg<1, false>(a, s);
+    if (ndim == 2) rc = per ? launch_cg<2, true>(a, s) : launch_cg<2, false>(a, s);
+    if (ndim == 3) rc = per ? launch_cg<3, true>(a, s) : launch_cg<3, false>(a, s);
+    return rc;
+}
+
+size_t sdcb200_newton_workspace_bytes(int n) { return work_layout(2, n, 6).total; }
+
+int sdcb200_allencahn_newton_solve(int n, double factor, double a_diag, double a_off, double inv_eps2, int nu_exp,
+                                   const double* rhs, double* u, double newton_tol, int newton_maxiter,
+                                   double lin_tol, int lin_maxiter, double inexact_ratio, void* work,
+                                   size_t work_bytes, int* counters_dev, void* stream) {
+    SDC_REQUIRE(n >= 2 && !(n & 1), "periodic grid needs an even number of points per dimension");
+    SDC_REQUIRE(nu_exp >= 1, "nu must be a positive integer");
+    const WorkLayout w = work_layout(2, n, 6);
+    SDC_REQUIRE(work != nullptr && work_bytes >= w.total, "workspace too small (see sdcb200_newton_workspace_bytes)");
+    SDC_REQUIRE((reinterpret_cast<size_t>(work) & 255u) == 0, "workspace must be 256-byte aligned");
+    SDC_REQUIRE(rhs && u && !(reinterpret_cast<size_t>(rhs) & 15u) && !(reinterpret_cast<size_t>(u) & 15u),
+                "rhs / u missing or misaligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    NewtonArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = make_geom(2, n, SDCB200_BC_PERIODIC);
+    a.factor = factor;
+    a.a_diag = a_diag;
+    a.a_off = a_off;
+    a.inv_eps2 = inv_eps2;
+    a.nu_exp = nu_exp;
+    a.rhs = rhs;
+    a.u = u;
+    char* base = static_cast<char*>(work);
+    auto fieldp = [&](int k) { return reinterpret_cast<double*>(base + w.fields_off + (size_t)k * w.field + w.guard_bytes); };
+    a.gvec = fieldp(0);
+    a.z = fieldp(1);
+    a.dvec = fieldp(2);
+    a.r = fieldp(3);
+    a.p = fieldp(4);
+    a.q = fieldp(5);
+    a.newton_tol = newton_tol;
+    a.lin_tol = lin_tol;
+    a.inexact_ratio = inexact_ratio;
+    a.newton_maxiter = newton_maxiter;
+    a.lin_maxiter = lin_maxiter;
+    a.partials = reinterpret_cast<double*>(base + w.partials_off);
+    a.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
+    a.counters_out = counters_dev;
+    SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    int grid = 0;
+    if (int rc = coresident_ctas(newton_kernel, &grid)) return rc;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    void* params[] = {&a};
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)newton_kernel, dim3(grid), dim3(kThreads), params, 0, s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,280 @@
+// K1 (collocation integration / rhs assembly / residual max-norm) and K6 (datatype utilities).
+// All kernels are single-pass, coalesced, double2-vectorised streaming kernels: HBM-bound, no tensor cores.
+#include "common.cuh"
+
+namespace sdcb200 {
+
+namespace {
+
+thread_local std::string g_last_error;
+int g_sm_count = 0;
+
+struct CollocArgs {
+    const double* in[SDCB200_MAX_TERMS];
+    double* out[SDCB200_MAX_NODES];
+    const double* add[SDCB200_MAX_NODES];
+    const double* u[SDCB200_MAX_NODES];
+    const double* base;
+    double W[SDCB200_MAX_NODES * SDCB200_MAX_TERMS];
+    double* resnorm;
+    long long count2;  // number of double2 elements
+    int nin;
+};
+
+// out[m] = base + sum_k W[m][k] in[k] + add[m]
+template <int NOUT>
+__global__ void __launch_bounds__(kThreads) colloc_apply_kernel(const __grid_constant__ CollocArgs a) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.count2; i += stride) {
+        double2 acc[NOUT];
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) acc[m] = make_double2(0.0, 0.0);
+#pragma unroll 4
+        for (int k = 0; k < a.nin; ++k) {
+            const double2 v = ld2(a.in[k] + 2 * i);
+#pragma unroll
+            for (int m = 0; m < NOUT; ++m) {
+                const double w = a.W[m * a.nin + k];
+                acc[m].x = fma(w, v.x, acc[m].x);
+                acc[m].y = fma(w, v.y, acc[m].y);
+            }
+        }
+        if (a.base != nullptr) {
+            const double2 b = ld2(a.base + 2 * i);
+#pragma unroll
+            for (int m = 0; m < NOUT; ++m) {
+                acc[m].x += b.x;
+                acc[m].y += b.y;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) {
+            if (a.add[m] != nullptr) {
+                const double2 t = ld2(a.add[m] + 2 * i);
+                acc[m].x += t.x;
+                acc[m].y += t.y;
+            }
+            st2(a.out[m] + 2 * i, acc[m]);
+        }
+    }
+}
+
+// res[m] = sum_k W[m][k] in[k] + (u0 - u[m]) + tau[m];  resnorm[m] = max |res[m]|
+template <int NOUT>
+__global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_constant__ CollocArgs a) {
+    __shared__ double scratch[33];
+    double vmax[NOUT];
+    unsigned bad = 0;  // bit m: a NaN was seen in res[m] (fmax would silently drop it; numpy's max would not)
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) vmax[m] = 0.0;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.count2; i += stride) {
+        double2 acc[NOUT];
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) acc[m] = make_double2(0.0, 0.0);
+#pragma unroll 4
+        for (int k = 0; k < a.nin; ++k) {
+            const double2 v = ld2(a.in[k] + 2 * i);
+#pragma unroll
+            for (int m = 0; m < NOUT; ++m) {
+                const double w = a.W[m * a.nin + k];
+                acc[m].x = fma(w, v.x, acc[m].x);
+                acc[m].y = fma(w, v.y, acc[m].y);
+            }
+        }
+        const double2 u0 = ld2(a.base + 2 * i);
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) {
+            const double2 um = ld2(a.u[m] + 2 * i);
+            acc[m].x += (u0.x - um.x);  // same association as sweeper.py:188  (res += u[0] - u[m+1])
+            acc[m].y += (u0.y - um.y);
+            if (a.add[m] != nullptr) {
+                const double2 t = ld2(a.add[m] + 2 * i);
+                acc[m].x += t.x;
+                acc[m].y += t.y;
+            }
+            if (a.out[m] != nullptr) st2(a.out[m] + 2 * i, acc[m]);
+            vmax[m] = fmax(vmax[m], fmax(fabs(acc[m].x), fabs(acc[m].y)));
+            if (acc[m].x != acc[m].x || acc[m].y != acc[m].y) bad |= 1u << m;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NOUT; ++m) {
+        const double v = block_max(vmax[m], scratch);
+        const double nanflag = block_max((bad >> m & 1u) ? 1.0 : 0.0, scratch);
+        if (threadIdx.x == 0) atomic_max_nonneg(a.resnorm + m, nanflag > 0.0 ? fabs(nan("")) : v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) maxabs_kernel(const double* __restrict__ x, long long count2, double* out) {
+    __shared__ double scratch[33];
+    double vmax = 0.0;
+    bool bad = false;
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < count2; i += stride) {
+        const double2 v = ld2(x + 2 * i);
+        vmax = fmax(vmax, fmax(fabs(v.x), fabs(v.y)));
+        bad |= (v.x != v.x) || (v.y != v.y);
+    }
+    const double nanflag = block_max(bad ? 1.0 : 0.0, scratch);
+    const double v = block_max(vmax, scratch);
+    if (threadIdx.x == 0) atomic_max_nonneg(out, nanflag > 0.0 ? fabs(nan("")) : v);
+}
+
+__global__ void __launch_bounds__(kThreads) axpby_kernel(long long count2, double a, const double* __restrict__ x,
+                                                          double b, const double* __restrict__ y, double* out) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < count2; i += stride) {
+        double2 v = ld2(x + 2 * i);
+        v.x *= a;
+        v.y *= a;
+        if (y != nullptr) {
+            const double2 w = ld2(y + 2 * i);
+            v.x = fma(b, w.x, v.x);
+            v.y = fma(b, w.y, v.y);
+        }
+        st2(out + 2 * i, v);
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15u) == 0; }
+
+inline int stream_grid(long long count2) {
+    const long long want = (count2 + kThreads - 1) / kThreads;
+    const long long cap = (long long)sm_count() * 8;  // a whole number of waves: 8 resident CTAs per SM
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(const char* where, const std::string& msg) {
+    g_last_error = std::string(where) + ": " + msg;
+    return 1;
+}
+int fail_cuda(const char* where, cudaError_t e) {
+    g_last_error = std::string(where) + ": CUDA error " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return 2;
+}
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+}  // namespace sdcb200
+
+using namespace sdcb200;
+
+extern "C" {
+
+int sdcb200_version(void) { return 100; }
+const char* sdcb200_last_error(void) { return g_last_error.c_str(); }
+
+long long sdcb200_pitch(int n) { return n + (n & 1); }
+long long sdcb200_volume(int ndim, int n) {
+    long long P = sdcb200_pitch(n), v = 1;
+    for (int d = 0; d < ndim; ++d) v *= P;
+    return v;
+}
+long long sdcb200_guard(int ndim, int n) {
+    long long P = sdcb200_pitch(n), g = 1;
+    for (int d = 1; d < ndim; ++d) g *= P;
+    return (g + 15) / 16 * 16;
+}
+
+int sdcb200_maxabs(const double* x, long long count, double* out_dev, void* stream) {
+    SDC_REQUIRE(count >= 0 && count % 2 == 0 && aligned16(x), "count must be even and x 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SDC_CUDA_OK(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+    if (count == 0) return 0;
+    maxabs_kernel<<<stream_grid(count / 2), kThreads, 0, s>>>(x, count / 2, out_dev);
+    SDC_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdcb200_axpby(long long count, double a, const double* x, double b, const double* y, double* out, void* stream) {
+    SDC_REQUIRE(count >= 0 && count % 2 == 0 && aligned16(x) && aligned16(y) && aligned16(out),
+                "count must be even and pointers 16-byte aligned");
+    if (count == 0) return 0;
+    axpby_kernel<<<stream_grid(count / 2), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(count / 2, a, x, b, y, out);
+    SDC_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdcb200_colloc_apply(long long count, int nout, int nin, const double* W_host, const double* const* in,
+                         const double* base, const double* const* add, double* const* out, void* stream) {
+    SDC_REQUIRE(nout >= 1 && nout <= SDCB200_MAX_NODES, "nout out of range");
+    SDC_REQUIRE(nin >= 0 && nin <= SDCB200_MAX_TERMS, "nin out of range");
+    SDC_REQUIRE(count >= 0 && count % 2 == 0, "count must be even");
+    CollocArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int k = 0; k < nin; ++k) {
+        SDC_REQUIRE(in[k] != nullptr && aligned16(in[k]), "input field missing or misaligned");
+        a.in[k] = in[k];
+    }
+    for (int m = 0; m < nout; ++m) {
+        SDC_REQUIRE(out[m] != nullptr && aligned16(out[m]), "output field missing or misaligned");
+        a.out[m] = out[m];
+        a.add[m] = add ? add[m] : nullptr;
+        SDC_REQUIRE(aligned16(a.add[m]), "add field misaligned");
+        for (int k = 0; k < nin; ++k) a.W[m * nin + k] = W_host[m * nin + k];
+    }
+    SDC_REQUIRE(aligned16(base), "base field misaligned");
+    a.base = base;
+    a.nin = nin;
+    a.count2 = count / 2;
+    if (count == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = stream_grid(a.count2);
+    switch (nout) {
+#define CASE(N) case N: colloc_apply_kernel<N><<<grid, kThreads, 0, s>>>(a); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    SDC_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdcb200_colloc_residual(long long count, int M, int nin, const double* W_host, const double* const* in,
+                            const double* u0, const double* const* u, const double* const* tau,
+                            double* const* res_out, double* resnorm_dev, void* stream) {
+    SDC_REQUIRE(M >= 1 && M <= SDCB200_MAX_NODES, "M out of range");
+    SDC_REQUIRE(nin >= 0 && nin <= SDCB200_MAX_TERMS, "nin out of range");
+    SDC_REQUIRE(count >= 0 && count % 2 == 0, "count must be even");
+    SDC_REQUIRE(u0 != nullptr && aligned16(u0), "u0 missing or misaligned");
+    CollocArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int k = 0; k < nin; ++k) {
+        SDC_REQUIRE(in[k] != nullptr && aligned16(in[k]), "input field missing or misaligned");
+        a.in[k] = in[k];
+    }
+    for (int m = 0; m < M; ++m) {
+        SDC_REQUIRE(u[m] != nullptr && aligned16(u[m]), "node value missing or misaligned");
+        a.u[m] = u[m];
+        a.add[m] = tau ? tau[m] : nullptr;
+        a.out[m] = res_out ? res_out[m] : nullptr;
+        SDC_REQUIRE(aligned16(a.add[m]) && aligned16(a.out[m]), "tau / residual field misaligned");
+        for (int k = 0; k < nin; ++k) a.W[m * nin + k] = W_host[m * nin + k];
+    }
+    a.base = u0;
+    a.nin = nin;
+    a.count2 = count / 2;
+    a.resnorm = resnorm_dev;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SDC_CUDA_OK(cudaMemsetAsync(resnorm_dev, 0, sizeof(double) * M, s));
+    if (count == 0) return 0;
+    const int grid = stream_grid(a.count2);
+    switch (M) {
+#define CASE(N) case N: colloc_residual_kernel<N><<<grid, kThreads, 0, s>>>(a); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    SDC_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+"""Problem classes of the sweep path with the reference's constructor keywords, attributes and error behaviour:
+
+* ``heatNd_unforced`` / ``heatNd_forced`` — ``pySDC/implementations/problem_classes/HeatEquation_ND_FD.py:8-230`` on top of
+  ``GenericNDimFinDiff`` (``generic_ND_FD.py:13-264``),
+* ``allencahn_fullyimplicit`` — ``problem_classes/AllenCahn_2D_FD.py:14-257``.
+
+The spatial operator is never assembled (the reference builds a scipy sparse matrix, 934 M non-zeros at 511^3): ``eval_f``
+is the matrix-free stencil kernel and ``solve_system`` the persistent CG / Newton kernels of ``libsdcb200``.  Besides the
+reference API the classes offer batched, in-place entry points (``eval_f_batch``, ``solve_system_batch``) that the
+sweepers use to update all M nodes with one launch when QDelta is diagonal.
+
+Classes are written as mix-ins; ``_bind(Problem)`` attaches them to a base class — the stand-alone one from
+``core.py`` here, pySDC's own in ``pysdc_plugin.py``.
+"""
+import numpy as np
+import torch
+
+from .backend import get_backend
+from .datatypes import imex_mesh, mesh
+from .layout import get_layout
+from .errors import ProblemError
+
+BC_CODES = {"dirichlet-zero": 0, "periodic": 1}
+
+
+def grid_1d(size, bc, left=0.0, right=1.0):
+    """Mesh width and 1-D grid (helpers/problem_helper.py:245-269)."""
+    L = right - left
+    if bc == "periodic":
+        dx = L / size
+        x = np.array([left + dx * i for i in range(size)])
+    elif "dirichlet" in bc or "neumann" in bc:
+        dx = L / (size + 1)
+        x = np.array([left + dx * (i + 1) for i in range(size)])
+    else:
+        raise NotImplementedError(f'Boundary conditions "{bc}" not implemented.')
+    return dx, x
+
+
+class DeviceWorkCounter:
+    """``WorkCounter`` (core/problem.py:16-40) whose count lives in a device int: the solver kernels add their
+    iteration counts without a host round trip; reading ``niter`` synchronises."""
+
+    def __init__(self, slot):
+        self._slot = slot  # 1-element int32 device tensor
+        self._host = 0
+
+    def __call__(self, *args, **kwargs):
+        self._host += 1
+
+    def decrement(self):
+        self._host -= 1
+
+    @property
+    def niter(self):
+        return int(self._slot.item()) + self._host
+
+    def __str__(self):
+        return f"{self.niter}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# heat equation
+# ---------------------------------------------------------------------------------------------------------------------
+class HeatMixin:
+    dtype_u = mesh
+    dtype_f = mesh
+    forced = False
+
+    def __init__(self, nvars=512, nu=0.1, freq=2, stencil_type="center", order=2, lintol=1e-12, liniter=10000,
+                 solver_type="direct", bc="periodic", sigma=6e-2):
+        # parameter checks of generic_ND_FD.py:99-133
+        if type(nvars) not in [int, tuple]:
+            raise ProblemError("nvars should be either tuple or int")
+        if type(freq) not in [int, tuple]:
+            raise ProblemError("freq should be either tuple or int")
+        if type(nvars) is int:
+            nvars = (nvars,)
+        ndim = len(nvars)
+        if ndim > 3:
+            raise ProblemError(f"can work with up to three dimensions, got {ndim}")
+        if type(freq) is int:
+            freq = (freq,) * ndim
+        if len(freq) != ndim:
+            raise ProblemError(f"len(freq)={len(freq)}, different to ndim={ndim}")
+        for f in freq:
+            if ndim == 1 and f == -1:
+                bc = "periodic"
+                break
+            if f % 2 != 0 and bc == "periodic":
+                raise ProblemError("need even number of frequencies due to periodic BCs")
+        for nvar in nvars:
+            if nvar % 2 != 0 and bc == "periodic":
+                raise ProblemError("the setup requires nvars = 2^p per dimension")
+            if (nvar + 1) % 2 != 0 and bc == "dirichlet-zero":
+                raise ProblemError("setup requires nvars = 2^p - 1")
+        if ndim > 1 and nvars[1:] != nvars[:-1]:
+            raise ProblemError("need a square domain, got %s" % (nvars,))
+        # what the device path implements
+        if bc not in BC_CODES:
+            raise ProblemError(f"boundary condition {bc!r} is not implemented on the device (have {list(BC_CODES)})")
+        if order != 2 or stencil_type != "center":
+            raise ProblemError("the device stencil is the order-2 centred Laplacian; "
+                               f"got order={order}, stencil_type={stencil_type!r}")
+        if solver_type not in ("CG", "direct"):
+            raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device (have 'CG', 'direct')")
+        if solver_type == "direct" and ndim > 1:
+            raise ProblemError("solver_type='direct' is implemented on the device for 1-D grids only; use 'CG'")
+
+        super().__init__(init=(nvars[0] if ndim == 1 else nvars, None, np.dtype("float64")))
+
+        dx, xvalues = grid_1d(nvars[0], bc)
+        self.xvalues = xvalues
+        self._makeAttributeAndRegister("nvars", "stencil_type", "order", "bc", localVars=locals(), readOnly=True)
+        self._makeAttributeAndRegister("freq", "lintol", "liniter", "solver_type", localVars=locals())
+        self._makeAttributeAndRegister("nu", localVars=locals(), readOnly=True)
+        self._makeAttributeAndRegister("sigma", localVars=locals())
+
+        # entries of A = nu * (kron-sum of [1, -2, 1]) / dx^2, formed in the order the reference forms them
+        # (problem_helper.py:239 divides by dx**2, generic_ND_FD.py:149 multiplies by the coefficient)
+        self.a_off = (1.0 / dx**2) * nu
+        self.a_diag = ((-2.0 * ndim) / dx**2) * nu
+        self._bc = BC_CODES[bc]
+        self._be = get_backend()
+        self._lay = get_layout(nvars)
+        self._counters = self._be.zeros(2 + 8, dtype=torch.int32)  # [total CG its, unused, per-system its of a solve]
+        self._work = {}
+        self._profile = None
+        if solver_type != "direct":
+            self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
+
+    # -- reference attributes -----------------------------------------------------------------------------------------
+    @property
+    def ndim(self):
+        return len(self.nvars)
+
+    @property
+    def dx(self):
+        return self.xvalues[1] - self.xvalues[0]
+
+    @property
+    def grids(self):
+        x = self.xvalues
+        if self.ndim == 1:
+            return x
+        if self.ndim == 2:
+            return x[None, :], x[:, None]
+        return x[None, :, None], x[:, None, None], x[None, None, :]
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import generic_implicit
+
+        return generic_implicit
+
+    # -- right-hand side ----------------------------------------------------------------------------------------------
+    def _spatial_profile(self):
+        """prod_d sin(pi k_d x_d) evaluated on the host with the reference's numpy expression (HeatEquation_ND_FD.py:
+        184-203) and uploaded once: the forcing is this profile times a scalar g(t), so no device sin is needed."""
+        if self._profile is None:
+            g = self.grids if self.ndim > 1 else (self.grids,)
+            prof = np.sin(np.pi * self.freq[0] * g[0])
+            for k, x in zip(self.freq[1:], g[1:]):
+                prof = prof * np.sin(np.pi * k * x)
+            m = mesh(self.init)
+            m[:] = np.broadcast_to(prof, self.nvars)
+            self._profile = m
+        return self._profile
+
+    def _forcing_factor(self, t):
+        return self.nu * np.pi**2 * sum([k**2 for k in self.freq]) * np.cos(t) - np.sin(t)
+
+    def eval_f_batch(self, us, ts, fs):
+        """fs[i] = f(us[i], ts[i]) in place, one launch for all fields."""
+        if self.forced:
+            self._be.heat_eval_f(self._lay, self._bc, self.a_diag, self.a_off, [u.flat for u in us],
+                                 [f.impl.flat for f in fs], self._spatial_profile().flat,
+                                 [self._forcing_factor(t) for t in ts], [f.expl.flat for f in fs])
+        else:
+            self._be.heat_eval_f(self._lay, self._bc, self.a_diag, self.a_off, [u.flat for u in us],
+                                 [f.flat for f in fs])
+
+    def eval_f(self, u, t):
+        """generic_ND_FD.py:188-206 / HeatEquation_ND_FD.py:162-204."""
+        f = self.f_init
+        self.eval_f_batch([u], [t], [f])
+        return f
+
+    # -- implicit solves ----------------------------------------------------------------------------------------------
+    def _cg_work(self, B):
+        if B not in self._work:
+            self._work[B] = self._be.cg_workspace(self._lay, B)
+        return self._work[B]
+
+    def solve_system_batch(self, rhs, factors, xs, ts=None):
+        """Solve (I - factors[i] A) xs[i] = rhs[i] in place (xs[i] holds the initial guess), all systems in one
+        persistent launch."""
+        m_diag = [1.0 - f * self.a_diag for f in factors]
+        m_off = [-(f * self.a_off) for f in factors]
+        if self.solver_type == "direct":
+            self._be.heat_direct_solve_1d(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs],
+                                          [x.flat for x in xs])
+            return
+        counters = self._counters[2: 2 + len(xs)]
+        counters.zero_()
+        log = getattr(self, "solve_log", None)  # bench.py: per-launch device timing + iteration counts
+        if log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        self._be.heat_cg_solve(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs], [x.flat for x in xs],
+                               self.lintol, self.liniter, self._cg_work(len(xs)), counters)
+        if log is not None:
+            ev1.record()
+            log.append((ev0, ev1, counters.clone()))
+        # the reference counts one callback per CG iteration of every solve
+        self._counters[0:1] += counters.sum(dtype=torch.int32)
+
+    def solve_system(self, rhs, factor, u0, t):
+        """generic_ND_FD.py:208-264: returns a new field, inputs untouched."""
+        sol = self.dtype_u(u0)
+        self.solve_system_batch([rhs], [factor], [sol], [t])
+        return sol
+
+    # -- exact solutions ----------------------------------------------------------------------------------------------
+    def u_exact(self, t, **kwargs):
+        ndim, freq, nu, sigma, dx = self.ndim, self.freq, self.nu, self.sigma, self.dx
+        sol = self.u_init
+        if self.forced:  # HeatEquation_ND_FD.py:206-230
+            g = self.grids if ndim > 1 else (self.grids,)
+            val = np.sin(np.pi * freq[0] * g[0])
+            for k, x in zip(freq[1:], g[1:]):
+                val = val * np.sin(np.pi * k * x)
+            sol[:] = np.broadcast_to(val * np.cos(t), self.nvars)
+            return sol
+        # HeatEquation_ND_FD.py:84-132
+        if ndim == 1:
+            x = self.grids
+            rho = (2.0 - 2.0 * np.cos(np.pi * freq[0] * dx)) / dx**2
+            if freq[0] > 0:
+                sol[:] = np.sin(np.pi * freq[0] * x) * np.exp(-t * nu * rho)
+            elif freq[0] == -1:
+                sol[:] = np.exp(-0.5 * ((x - 0.5) / sigma) ** 2) * np.exp(-t * nu * rho)
+        elif ndim == 2:
+            rho = (2.0 - 2.0 * np.cos(np.pi * freq[0] * dx)) / dx**2 + (2.0 - 2.0 * np.cos(np.pi * freq[1] * dx)) / dx**2
+            x, y = self.grids
+            sol[:] = np.sin(np.pi * freq[0] * x) * np.sin(np.pi * freq[1] * y) * np.exp(-t * nu * rho)
+        else:
+            # the middle term lacks /dx**2 in the reference (:119-123); kept so that u_exact is identical
+            rho = ((2.0 - 2.0 * np.cos(np.pi * freq[0] * dx)) / dx**2 + (2.0 - 2.0 * np.cos(np.pi * freq[1] * dx))
+                   + (2.0 - 2.0 * np.cos(np.pi * freq[2] * dx)) / dx**2)
+            x, y, z = self.grids
+            sol[:] = (np.sin(np.pi * freq[0] * x) * np.sin(np.pi * freq[1] * y) * np.sin(np.pi * freq[2] * z)
+                      * np.exp(-t * nu * rho))
+        return sol
+
+
+class HeatForcedMixin(HeatMixin):
+    dtype_f = imex_mesh
+    forced = True
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import imex_1st_order
+
+        return imex_1st_order
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Allen-Cahn, fully implicit
+# ---------------------------------------------------------------------------------------------------------------------
+class AllenCahnMixin:
+    dtype_u = mesh
+    dtype_f = mesh
+    forced = False
+
+    def __init__(self, nvars=(128, 128), nu=2, eps=0.04, newton_maxiter=200, newton_tol=1e-12, lin_tol=1e-8,
+                 lin_maxiter=100, inexact_linear_ratio=None, radius=0.25, order=2):
+        if len(nvars) != 2:
+            raise ProblemError("this is a 2d example, got %s" % (nvars,))
+        if nvars[0] != nvars[1]:
+            raise ProblemError("need a square domain, got %s" % (nvars,))
+        if nvars[0] % 2 != 0:
+            raise ProblemError("the setup requires nvars = 2^p per dimension")
+        if order != 2:
+            raise ProblemError(f"the device stencil is the order-2 centred Laplacian; got order={order}")
+        if int(nu) != nu or nu < 1:
+            raise ProblemError(f"the device path implements integer exponents nu >= 1, got {nu}")
+        nvars = tuple(nvars)
+        super().__init__((nvars, None, np.dtype("float64")))
+        self._makeAttributeAndRegister("nvars", "nu", "eps", "radius", "order", localVars=locals(), readOnly=True)
+        self._makeAttributeAndRegister("newton_maxiter", "newton_tol", "lin_tol", "lin_maxiter", "inexact_linear_ratio",
+                                       localVars=locals(), readOnly=False)
+        self.dx = 1.0 / self.nvars[0]
+        self.xvalues = np.array([i * self.dx - 0.5 for i in range(self.nvars[0])])
+        self.a_off = 1.0 / self.dx**2
+        self.a_diag = (-2.0 * 2) / self.dx**2
+        self._be = get_backend()
+        self._lay = get_layout(nvars)
+        self._counters = self._be.zeros(4, dtype=torch.int32)  # [newton, linear, rhs(unused), scratch]
+        self._work = None
+        self.newton_itercount = 0  # kept for API compatibility; the live counts are in work_counters
+        self.lin_itercount = 0
+        self.newton_ncalls = 0
+        self.lin_ncalls = 0
+        self.work_counters["newton"] = DeviceWorkCounter(self._counters[0:1])
+        self.work_counters["rhs"] = DeviceWorkCounter(self._counters[2:3])
+        self.work_counters["linear"] = DeviceWorkCounter(self._counters[1:2])
+
+    @property
+    def ndim(self):
+        return 2
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import generic_implicit
+
+        return generic_implicit
+
+    def eval_f_batch(self, us, ts, fs):
+        self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
+                                  [u.flat for u in us], [f.flat for f in fs])
+        for _ in us:
+            self.work_counters["rhs"]()
+
+    def eval_f(self, u, t):
+        """AllenCahn_2D_FD.py:207-228."""
+        f = self.dtype_f(self.init)
+        self.eval_f_batch([u], [t], [f])
+        return f
+
+    def solve_system_batch(self, rhs, factors, xs, ts=None):
+        """Newton + inner CG per system, in place on xs (AllenCahn_2D_FD.py:137-205); one persistent launch each."""
+        if self._work is None:
+            self._work = self._be.newton_workspace(self._lay)
+        for r, fac, x in zip(rhs, factors, xs):
+            self._be.allencahn_newton_solve(self._lay, fac, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
+                                            r.flat, x.flat, self.newton_tol, self.newton_maxiter, self.lin_tol,
+                                            self.lin_maxiter, self.inexact_linear_ratio, self._work,
+                                            self._counters[0:2])
+            self.newton_ncalls += 1
+
+    def solve_system(self, rhs, factor, u0, t):
+        me = self.dtype_u(u0)
+        self.solve_system_batch([rhs], [factor], [me], [t])
+        return me
+
+    def u_exact(self, t, u_init=None, t_init=None):
+        """AllenCahn_2D_FD.py:230-257; only the initial condition (t = 0) is available without a reference integrator."""
+        me = self.dtype_u(self.init, val=0.0)
+        if t > 0:
+            raise NotImplementedError("u_exact(t > 0) needs the reference's scipy reference solution; not on the device")
+        X, Y = np.meshgrid(self.xvalues, self.xvalues)
+        me[:] = np.tanh((self.radius - np.sqrt(X**2 + Y**2)) / (np.sqrt(2) * self.eps))
+        return me
+
+
+def _bind(base):
+    """Concrete problem classes over a given ``Problem`` base class."""
+    ns = {}
+    for name, mixin in (("heatNd_unforced", HeatMixin), ("heatNd_forced", HeatForcedMixin),
+                        ("allencahn_fullyimplicit", AllenCahnMixin)):
+        ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
+    return ns
+
+
+from .core import Problem as _Problem  # noqa: E402
+
+globals().update(_bind(_Problem))

@@ -1,0 +1,251 @@
+"""SDC sweepers ``generic_implicit`` and ``imex_1st_order`` on the device.
+
+Same class names, constructor, attributes (``coll``, ``QI``, ``QE``, ``params``) and methods as the reference
+(``pySDC/implementations/sweeper_classes/generic_implicit.py``, ``imex_1st_order.py``, base ``pySDC/core/sweeper.py``):
+``predict``, ``integrate``, ``update_nodes``, ``compute_residual``, ``compute_end_point``.  They read and write only
+``L.u, L.f, L.tau, L.uend, L.residual, L.status.{residual, updated, unlocked}`` like the originals, so the reference's
+controllers, transfer classes and convergence controllers can drive them unchanged.
+
+What changes is how the work is done:
+
+* all "known terms" of a sweep — ``u0 + dt (Q - QDelta) F(u^k) + tau`` for every node (generic_implicit.py:70-82) — are
+  one launch of the fused collocation kernel (each of the M*C right-hand sides read once, M results written once)
+  instead of ~2M^2 axpy passes with temporaries;
+* when QDelta is diagonal (MIN-SR-NS, MIN-SR-FLEX, IEpar, ...; ``sweeper.parallelizable``, core/sweeper.py:108-109) the M
+  node systems are independent: they are solved by ONE persistent batched-CG launch and their right-hand sides are
+  re-evaluated by one stencil launch; lower-triangular QDelta (LU, IE) keeps the sequential node order of
+  generic_implicit.py:85-98 with one solve launch per node;
+* the residual (core/sweeper.py:164-215) is one fused pass producing the M max-norms on the device; the single
+  device->host read of a sweep happens here, because ``L.status.residual`` has to be a Python float for
+  ``CheckConvergence`` (convergence_controller_classes/check_convergence.py:75-76).
+
+Solutions and right-hand sides are updated in place in the buffers ``L.u[m]`` / ``L.f[m]`` already own.
+"""
+import numpy as np
+import torch
+
+from .backend import get_backend
+from .errors import ParameterError
+
+
+class _SweepCommon:
+    """Methods shared by both sweepers; ``self.coll / self.params / self.level / self.QI`` come from the base class."""
+
+    imex = False
+
+    # ---- helpers ----------------------------------------------------------------------------------------------------
+    def _f_inputs(self, L, first=1):
+        """Flat device views of f[first..M], node-major then component (impl, expl)."""
+        ins = []
+        for j in range(first, self.coll.num_nodes + 1):
+            f = L.f[j]
+            if self.imex:
+                ins += [f.impl.flat, f.expl.flat]
+            else:
+                ins.append(f.flat)
+        return ins
+
+    def _expand(self, WI, WE=None):
+        """(rows x M) coefficient blocks -> (rows x M*C) matching ``_f_inputs`` ordering."""
+        if not self.imex:
+            return np.ascontiguousarray(WI)
+        WE = WI if WE is None else WE
+        out = np.empty((WI.shape[0], 2 * WI.shape[1]))
+        out[:, 0::2] = WI
+        out[:, 1::2] = WE
+        return out
+
+    def _scratch(self, L, count):
+        """M reusable right-hand-side fields per level (never visible to the caller)."""
+        key = (id(L), L.prob.init[0])
+        pool = self.__dict__.setdefault("_rhs_pool", {})
+        if key not in pool or len(pool[key]) < count:
+            pool[key] = [L.prob.dtype_u(L.prob.init) for _ in range(count)]
+        return pool[key]
+
+    # ---- predictor (core/sweeper.py:125-162) ------------------------------------------------------------------------
+    def predict(self):
+        L = self.level
+        P = L.prob
+        M = self.coll.num_nodes
+        guess = self.params.initial_guess
+        times = [L.time] + [L.time + L.dt * self.coll.nodes[m] for m in range(M)]
+        if guess == "spread":
+            for m in range(1, M + 1):
+                L.u[m] = P.dtype_u(L.u[0])
+            if hasattr(P, "eval_f_batch"):
+                for m in range(M + 1):
+                    L.f[m] = P.dtype_f(P.init)
+                P.eval_f_batch(L.u, times, L.f)
+            else:
+                for m in range(M + 1):
+                    L.f[m] = P.eval_f(L.u[m], times[m])
+        elif guess in ("copy", "zero", "random"):
+            L.f[0] = P.eval_f(L.u[0], L.time)
+            for m in range(1, M + 1):
+                if guess == "copy":
+                    L.u[m] = P.dtype_u(L.u[0])
+                    L.f[m] = P.dtype_f(L.f[0])
+                elif guess == "zero":
+                    L.u[m] = P.dtype_u(init=P.init, val=0.0)
+                    L.f[m] = P.dtype_f(init=P.init, val=0.0)
+                else:
+                    L.u[m] = P.dtype_u(init=P.init, val=self.rng.rand(1)[0])
+                    L.f[m] = P.dtype_f(init=P.init, val=self.rng.rand(1)[0])
+        else:
+            raise ParameterError(f"initial_guess option {guess} not implemented")
+        L.status.unlocked = True
+        L.status.updated = True
+
+    # ---- integrate (generic_implicit.py:29-49, imex_1st_order.py:37-55) ---------------------------------------------
+    def integrate(self):
+        L = self.level
+        P = L.prob
+        M = self.coll.num_nodes
+        me = [P.dtype_u(P.init) for _ in range(M)]
+        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
+        get_backend().colloc_apply(W, self._f_inputs(L), None, None, [x.flat for x in me])
+        return me
+
+    # ---- one sweep (generic_implicit.py:51-103, imex_1st_order.py:57-108) -------------------------------------------
+    def update_nodes(self):
+        L = self.level
+        P = L.prob
+        assert L.status.unlocked
+        be = get_backend()
+        M = self.coll.num_nodes
+        dt = L.dt
+        Q, QI = self.coll.Qmat, self.QI
+        QE = self.QE if self.imex else None
+        times = [L.time + dt * self.coll.nodes[m] for m in range(M)]
+        alphas = [dt * QI[m + 1, m + 1] for m in range(M)]
+        batched = hasattr(P, "solve_system_batch") and hasattr(P, "eval_f_batch")
+
+        # known terms of every node: u0 + dt*(Q - QDelta) F(u^k) + tau, one fused pass
+        rhs = self._scratch(L, M)
+        W = self._expand(dt * (Q[1:, 1:] - QI[1:, 1:]), None if QE is None else dt * (Q[1:, 1:] - QE[1:, 1:]))
+        taus = [None if t is None else t.flat for t in L.tau]
+        be.colloc_apply(W, self._f_inputs(L), L.u[0].flat, taus if any(t is not None for t in taus) else None,
+                        [r.flat for r in rhs])
+
+        strictly_lower_empty = not np.any(np.tril(QI[1:, 1:], k=-1)) and (QE is None or not np.any(np.tril(QE[1:, 1:], k=-1)))
+        if batched and strictly_lower_empty and (self.imex or all(a != 0 for a in alphas)):
+            # diagonal QDelta: the M node systems are independent -> one batched solve, one batched f evaluation
+            us, fs = L.u[1:], L.f[1:]
+            P.solve_system_batch(rhs[:M], alphas, us, times)
+            P.eval_f_batch(us, times, fs)
+        else:
+            for m in range(M):
+                if m > 0:
+                    # add dt*QDelta[m+1, j] f(u_j^{k+1}) for the nodes j <= m already updated in this sweep
+                    Wn = self._expand(dt * QI[m + 1: m + 2, 1: m + 1], None if QE is None else dt * QE[m + 1: m + 2, 1: m + 1])
+                    if np.any(Wn):
+                        ins = self._f_inputs(L)[: Wn.shape[1]]
+                        be.colloc_apply(Wn, ins, rhs[m].flat, None, [rhs[m].flat])
+                if alphas[m] == 0 and not self.imex:
+                    L.u[m + 1][:] = rhs[m]  # generic_implicit.py:93-94
+                elif batched:
+                    P.solve_system_batch([rhs[m]], [alphas[m]], [L.u[m + 1]], [times[m]])
+                else:
+                    L.u[m + 1] = P.solve_system(rhs[m], alphas[m], L.u[m + 1], times[m])
+                if batched:
+                    P.eval_f_batch([L.u[m + 1]], [times[m]], [L.f[m + 1]])
+                else:
+                    L.f[m + 1] = P.eval_f(L.u[m + 1], times[m])
+        L.status.updated = True
+        return None
+
+    # ---- residual (core/sweeper.py:164-215) -------------------------------------------------------------------------
+    def compute_residual(self, stage=""):
+        L = self.level
+        if stage in self.params.skip_residual_computation:
+            L.status.residual = 0.0 if L.status.residual is None else L.status.residual
+            return None
+        be = get_backend()
+        M = self.coll.num_nodes
+        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
+        taus = [None if t is None else t.flat for t in L.tau]
+        res_out = None
+        if getattr(self.params, "store_residual", False):
+            L.residual = [L.prob.dtype_u(L.prob.init) for _ in range(M)]
+            res_out = [r.flat for r in L.residual]
+        if "_resnorm" not in self.__dict__:
+            self._resnorm = be.zeros(9)
+        norms_dev = self._resnorm
+        be.colloc_residual(W, self._f_inputs(L), L.u[0].flat, [u.flat for u in L.u[1:]],
+                           taus if any(t is not None for t in taus) else None, res_out, norms_dev[:M])
+        rtype = L.params.residual_type
+        if rtype.endswith("_rel"):
+            be.maxabs_async(L.u[0].vol, norms_dev[8:9])
+        host = norms_dev.cpu().tolist()  # the one device->host read of a sweep
+        res_norm, u0_norm = host[:M], host[8]
+        comm = L.u[0].comm
+        if comm is not None and getattr(comm, "size", 1) > 1:
+            from .comm import MAX
+            res_norm = comm.allreduce(res_norm, op=MAX)
+            u0_norm = comm.allreduce(u0_norm, op=MAX)
+        if rtype == "full_abs":
+            L.status.residual = max(res_norm)
+        elif rtype == "last_abs":
+            L.status.residual = res_norm[-1]
+        elif rtype == "full_rel":
+            L.status.residual = max(res_norm) / u0_norm
+        elif rtype == "last_rel":
+            L.status.residual = res_norm[-1] / u0_norm
+        else:
+            raise ParameterError(f"residual_type = {rtype} not implemented, choose full_abs, last_abs, full_rel or "
+                                 "last_rel instead")
+        L.status.updated = False
+        return None
+
+    # ---- end point (generic_implicit.py:105-131, imex_1st_order.py:110-137) -----------------------------------------
+    def compute_end_point(self):
+        L = self.level
+        P = L.prob
+        if self.coll.right_is_node and not self.params.do_coll_update:
+            L.uend = P.dtype_u(L.u[-1])
+        else:
+            L.uend = P.dtype_u(P.init)
+            W = self._expand((L.dt * self.coll.weights)[None, :])
+            tau = None if L.tau[-1] is None else [L.tau[-1].flat]
+            get_backend().colloc_apply(W, self._f_inputs(L), L.u[0].flat, tau, [L.uend.flat])
+        return None
+
+
+class GenericImplicitMixin(_SweepCommon):
+    """generic_implicit.py:4-27."""
+
+    imex = False
+
+    def __init__(self, params, level):
+        if "QI" not in params:
+            params["QI"] = "IE"
+        super().__init__(params, level)
+        self.QI = self.get_Qdelta_implicit(qd_type=self.params.QI)
+
+
+class Imex1stOrderMixin(_SweepCommon):
+    """imex_1st_order.py:6-35."""
+
+    imex = True
+
+    def __init__(self, params, level):
+        if "QI" not in params:
+            params["QI"] = "IE"
+        if "QE" not in params:
+            params["QE"] = "EE"
+        super().__init__(params, level)
+        self.QI = self.get_Qdelta_implicit(qd_type=self.params.QI)
+        self.QE = self.get_Qdelta_explicit(qd_type=self.params.QE)
+
+
+def _bind(base):
+    ns = {}
+    for name, mixin in (("generic_implicit", GenericImplicitMixin), ("imex_1st_order", Imex1stOrderMixin)):
+        ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
+    return ns
+
+
+from .core import Sweeper as _Sweeper  # noqa: E402
+
+globals().update(_bind(_Sweeper))

@@ -1,0 +1,179 @@
+"""TEST-ONLY numpy stand-in for ``pysdc_b200.backend.CudaBackend``.
+
+It lets the CPU test-suite (no GPU in the build container) drive the *host* logic of the package — datatypes, problem
+classes, sweepers, controller, the pySDC plug-in — end to end against the golden fixtures.  It is never imported by the
+package; the product backend raises ``BackendError`` when the CUDA library or a GPU is missing.  Each method mirrors the
+semantics of the C entry point of the same name in ``include/sdc_b200.h`` (plain numpy, independent of ``oracle/``).
+"""
+import numpy as np
+import torch
+
+
+def _np(t):
+    return t.numpy()  # CPU tensors share memory with numpy
+
+
+class NumpyBackend:
+    name = "numpy-test-double"
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.launches = 0
+
+    def zeros(self, count, dtype=torch.float64):
+        return torch.zeros(count, dtype=dtype)
+
+    def synchronize(self):
+        pass
+
+    def device_info(self):
+        return dict(sm_count=0, cc=(0, 0), solver_ctas=0)
+
+    # ---- helpers ----------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _grid(lay, t):
+        """Writable numpy view of the grid points of a flat volume tensor."""
+        return _np(lay.interior(t))
+
+    @staticmethod
+    def _lap_sum(x, periodic):
+        """Sum of the 2*ndim neighbours (zero outside for Dirichlet)."""
+        out = np.zeros_like(x)
+        for ax in range(x.ndim):
+            if periodic:
+                out += np.roll(x, 1, axis=ax) + np.roll(x, -1, axis=ax)
+            else:
+                lo = [slice(None)] * x.ndim
+                hi = [slice(None)] * x.ndim
+                lo[ax], hi[ax] = slice(1, None), slice(None, -1)
+                out[tuple(lo)] += x[tuple(hi)]
+                out[tuple(hi)] += x[tuple(lo)]
+        return out
+
+    # ---- K6 ---------------------------------------------------------------------------------------------------------
+    def maxabs_async(self, x, out):
+        self.launches += 1
+        out[0] = float(np.max(np.abs(_np(x)))) if x.numel() else 0.0
+
+    def maxabs(self, x):
+        out = torch.zeros(1, dtype=torch.float64)
+        self.maxabs_async(x, out)
+        return float(out[0])
+
+    def axpby(self, a, x, b, y, out):
+        self.launches += 1
+        r = a * _np(x)
+        if y is not None:
+            r = r + b * _np(y)
+        _np(out)[:] = r
+
+    # ---- K1 ---------------------------------------------------------------------------------------------------------
+    def colloc_apply(self, W, ins, base, adds, outs):
+        self.launches += 1
+        W = np.asarray(W, dtype=float).reshape(len(outs), len(ins))
+        vals = [_np(t).copy() for t in ins]
+        b = None if base is None else _np(base).copy()
+        for m, o in enumerate(outs):
+            acc = np.zeros(o.numel())
+            for k, v in enumerate(vals):
+                acc += W[m, k] * v
+            if b is not None:
+                acc += b
+            if adds is not None and adds[m] is not None:
+                acc += _np(adds[m])
+            _np(o)[:] = acc
+
+    def colloc_residual(self, W, ins, u0, us, taus, res_outs, resnorm):
+        self.launches += 1
+        W = np.asarray(W, dtype=float).reshape(len(us), len(ins))
+        vals = [_np(t) for t in ins]
+        for m, u in enumerate(us):
+            acc = np.zeros(u.numel())
+            for k, v in enumerate(vals):
+                acc += W[m, k] * v
+            acc += _np(u0) - _np(u)
+            if taus is not None and taus[m] is not None:
+                acc += _np(taus[m])
+            if res_outs is not None and res_outs[m] is not None:
+                _np(res_outs[m])[:] = acc
+            resnorm[m] = float(np.max(np.abs(acc)))
+
+    # ---- K2 ---------------------------------------------------------------------------------------------------------
+    def heat_eval_f(self, lay, bc, a_diag, a_off, us, fs, profile=None, gts=None, fexpls=None):
+        self.launches += 1
+        for i, (u, f) in enumerate(zip(us, fs)):
+            x = self._grid(lay, u)
+            self._grid(lay, f)[...] = a_diag * x + a_off * self._lap_sum(x, bc == 1)
+            if profile is not None:
+                self._grid(lay, fexpls[i])[...] = self._grid(lay, profile) * gts[i]
+
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs):
+        self.launches += 1
+        for u, f in zip(us, fs):
+            x = self._grid(lay, u)
+            self._grid(lay, f)[...] = a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)
+
+    # ---- K3 / K4 ----------------------------------------------------------------------------------------------------
+    def cg_workspace(self, lay, B):
+        return torch.zeros(8, dtype=torch.float64)
+
+    newton_workspace = lambda self, lay: torch.zeros(8, dtype=torch.float64)  # noqa: E731
+
+    def _cg(self, matvec, b, x, rtol, maxiter):
+        """scipy.sparse.linalg.cg's recurrence (atol = rtol*||b||, test before each iteration)."""
+        bnrm = np.linalg.norm(b)
+        if bnrm == 0:
+            x[...] = b
+            return 0
+        atol = rtol * bnrm
+        r = b - matvec(x)
+        p, rho_prev, its = None, None, 0
+        for it in range(maxiter):
+            if np.linalg.norm(r) < atol:
+                return its
+            rho = np.vdot(r, r)
+            p = r.copy() if it == 0 else r + (rho / rho_prev) * p
+            q = matvec(p)
+            alpha = rho / np.vdot(p, q)
+            x += alpha * p
+            r -= alpha * q
+            rho_prev = rho
+            its += 1
+        return its
+
+    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+        self.launches += 1
+        for b, (r, x) in enumerate(zip(rhs, xs)):
+            mv = lambda v, b=b: m_diag[b] * v + m_off[b] * self._lap_sum(v, bc == 1)  # noqa: E731
+            iters_dev[b] += self._cg(mv, self._grid(lay, r).copy(), self._grid(lay, x), rtol, maxiter)
+
+    def heat_direct_solve_1d(self, lay, bc, m_diag, m_off, rhs, xs):
+        self.launches += 1
+        n = lay.n
+        for b, (r, x) in enumerate(zip(rhs, xs)):
+            Mx = m_diag[b] * np.eye(n) + m_off[b] * (np.eye(n, k=1) + np.eye(n, k=-1))
+            if bc == 1:
+                Mx[0, -1] += m_off[b]
+                Mx[-1, 0] += m_off[b]
+            self._grid(lay, x)[...] = np.linalg.solve(Mx, self._grid(lay, r))
+
+    def allencahn_newton_solve(self, lay, factor, a_diag, a_off, inv_eps2, nu_exp, rhs, u, newton_tol, newton_maxiter,
+                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
+        self.launches += 1
+        x = self._grid(lay, u)
+        b = self._grid(lay, rhs)
+        n = 0
+        while n < newton_maxiter:
+            g = x - factor * (a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)) - b
+            res = np.max(np.abs(g))
+            if inexact_ratio:
+                lin_tol = res * inexact_ratio
+            if res < newton_tol:
+                break
+            d = 1.0 - factor * (a_diag + inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp))
+            mv = lambda v: d * v - factor * a_off * self._lap_sum(v, True)  # noqa: E731
+            z = np.zeros_like(x)
+            counters_dev[1] += self._cg(mv, g, z, lin_tol, lin_maxiter)
+            x -= z
+            n += 1
+        counters_dev[0] += n

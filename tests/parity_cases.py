@@ -1,0 +1,181 @@
+"""Parity checks shared by the CPU suite (numpy test double for the kernel library: host logic only) and the GPU
+suite (the real CUDA library through the C ABI).  Every check compares the package's classes with fixtures generated
+by the unmodified reference (oracle/make_golden.py) and, where it needs fresh inputs, with the CPU oracle.
+
+Tolerances (stated once, used everywhere):
+  * eval_f, collocation integrals, end point: 1e-13 relative to the field's max-norm (pure stencil / axpy arithmetic,
+    differences are summation order and FMA contraction only);
+  * anything downstream of an iterative solve: 1e-10 relative (north_star: "end-of-step solution must agree to <= 1e-10
+    relative error when both sides solve to the same lintol");
+  * SDC iteration counts: identical.  CG / Newton work counters: identical up to +-1 per solve (the stopping test
+    ||r|| < rtol*||b|| sits on a rounding-sensitive threshold), asserted as a relative band of 2 %.
+"""
+import numpy as np
+
+from conftest import load_golden
+
+TOL_ARITH = 1e-13
+TOL_SOLVE = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def stencil_tol(P, u_max, f_ref):
+    """Absolute tolerance for f = A u: a few ulps of the largest term of the stencil sum (|a_diag| * max|u|), which
+    for smooth fields is orders of magnitude larger than f itself (cancellation)."""
+    return 8 * np.finfo(float).eps * (abs(P.a_diag) * u_max + float(np.max(np.abs(f_ref))))
+
+
+def classes():
+    from pysdc_b200 import problems, sweepers
+
+    return ({"heatNd_unforced": problems.heatNd_unforced, "heatNd_forced": problems.heatNd_forced,
+             "allencahn_fullyimplicit": problems.allencahn_fullyimplicit},
+            {"generic_implicit": sweepers.generic_implicit, "imex_1st_order": sweepers.imex_1st_order})
+
+
+def tuplify(pp):
+    pp = dict(pp)
+    for k in ("nvars", "freq"):
+        if isinstance(pp.get(k), list):
+            pp[k] = tuple(pp[k])
+    return pp
+
+
+def make_description(spec):
+    probs, sweeps = classes()
+    return dict(problem_class=probs[spec["problem"]], problem_params=tuplify(spec["problem_params"]),
+                sweeper_class=sweeps[spec["sweeper"]], sweeper_params=dict(spec["sweeper_params"]),
+                level_params=dict(spec["level_params"]), step_params=dict(spec["step_params"]))
+
+
+def to_mesh(P, arr, dtype=None):
+    m = (dtype or P.dtype_u)(P.init)
+    m[:] = arr
+    return m
+
+
+def close_counts(got, want, slack=0.02):
+    got, want = np.atleast_1d(got), np.atleast_1d(want)
+    return bool(np.all(np.abs(got - want) <= np.maximum(np.ceil(slack * want), 1)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def check_operator(name):
+    spec, g = load_golden(name)
+    probs, _ = classes()
+    P = probs[spec["problem"]](**tuplify(spec["problem_params"]))
+    u = to_mesh(P, g["u"])
+    rhs = to_mesh(P, g["rhs"])
+    u_before, rhs_before = u.get().copy(), rhs.get().copy()
+    f = P.eval_f(u, spec["t"])
+    assert type(f) is P.dtype_f
+    assert f.shape == g["f"].shape
+    assert np.max(np.abs(f.get() - g["f"])) <= stencil_tol(P, np.max(np.abs(g["u"])), g["f"])
+    sol = P.solve_system(rhs, spec["factor"], u, spec["t"])
+    assert type(sol) is P.dtype_u
+    assert relerr(sol.get(), g["sol"]) < TOL_SOLVE
+    # inputs are not mutated (generic_ND_FD.py:208-264 returns a fresh field)
+    assert np.array_equal(u.get(), u_before) and np.array_equal(rhs.get(), rhs_before)
+    if "cg_iters" in g:
+        assert close_counts(P.work_counters["CG"].niter, int(g["cg_iters"]))
+    else:
+        assert P.work_counters["newton"].niter == int(g["newton"])
+        assert close_counts(P.work_counters["linear"].niter, int(g["linear"]))
+        assert P.work_counters["rhs"].niter == 1
+    t_ex = 0.0 if spec["problem"] == "allencahn_fullyimplicit" else 0.1
+    assert relerr(P.u_exact(t_ex).get(), g["u_exact"]) == 0.0  # host numpy expression, then upload
+
+
+def check_sweep_dump(name):
+    from pysdc_b200.core import Step
+
+    spec, g = load_golden(name)
+    S = Step(make_description(spec))
+    L = S.levels[0]
+    P = L.prob
+    L.status.time = spec["t0"]
+    np.testing.assert_allclose(L.sweep.coll.Qmat, g["Qmat"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(L.sweep.coll.nodes, g["nodes"], rtol=0, atol=1e-15)
+    S.init_step(to_mesh(P, g["u0"]))
+    L.sweep.predict()
+    assert L.status.unlocked and L.status.updated
+    if "tau" in g:
+        L.tau = [to_mesh(P, t) for t in g["tau"]]
+    f_pred = np.stack([f.get() for f in L.f])
+    assert np.max(np.abs(f_pred - g["f_pred"])) <= stencil_tol(P, np.max(np.abs(g["u0"])), g["f_pred"])
+    L.sweep.compute_residual()
+    assert isinstance(L.status.residual, float) and not L.status.updated
+    assert abs(L.status.residual - float(g["res_pred"])) <= 1e-12 * max(1.0, abs(float(g["res_pred"])))
+    k = 1
+    while f"u_sweep{k}" in g:
+        L.status.sweep = k
+        L.sweep.updateVariableCoeffs(k)
+        u_ids = [id(u) for u in L.u]
+        L.sweep.update_nodes()
+        assert L.status.updated
+        assert relerr(np.stack([u.get() for u in L.u]), g[f"u_sweep{k}"]) < TOL_SOLVE, k
+        assert relerr(np.stack([f.get() for f in L.f]), g[f"f_sweep{k}"]) < 10 * TOL_SOLVE, k
+        integ = L.sweep.integrate()
+        assert len(integ) == L.sweep.coll.num_nodes and all(type(i) is P.dtype_u for i in integ)
+        assert relerr(np.stack([i.get() for i in integ]), g[f"integrate_sweep{k}"]) < 10 * TOL_SOLVE
+        for rt in ("full_abs", "last_abs", "full_rel", "last_rel"):
+            L.params.residual_type = rt
+            L.sweep.compute_residual()
+            want = float(g[f"res_{rt}_sweep{k}"])
+            # the residual is a difference of O(1) quantities each carrying the 1e-10 solve tolerance
+            assert abs(L.status.residual - want) <= 1e-9 * max(abs(float(g["res_pred"])), 1.0), (rt, k)
+        L.params.residual_type = "full_abs"
+        assert len(u_ids) == len(L.u)
+        k += 1
+    np.testing.assert_allclose(L.sweep.QI, g["QI"], rtol=0, atol=1e-14)
+    L.sweep.compute_end_point()
+    assert type(L.uend) is P.dtype_u
+    assert relerr(L.uend.get(), g["uend"]) < TOL_SOLVE
+    for key in P.work_counters:
+        want = int(g["work_" + key])
+        if key in ("newton", "rhs"):
+            assert P.work_counters[key].niter == want, key
+        else:
+            assert close_counts(P.work_counters[key].niter, want), (key, P.work_counters[key].niter, want)
+
+
+def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
+    from pysdc_b200.controller import LogWork, controller_nonMPI
+    from pysdc_b200.stats import get_sorted
+
+    spec, g = load_golden(name)
+    d = make_description(spec)
+    c = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40, "hook_class": [LogWork]}, description=d)
+    P = c.MS[0].levels[0].prob
+    if spec["u0"] == "exact":
+        u0 = P.u_exact(spec["t0"])
+    else:
+        u0 = to_mesh(P, np.random.default_rng(spec["seed"]).standard_normal(P.nvars))
+    uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+    niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
+    assert niter == g["niter"].tolist(), (niter, g["niter"].tolist())
+    times = [t for t, _ in get_sorted(stats, type="niter", sortby="time")]
+    for t, ref in zip(times, g["residuals"]):
+        hist = [v for _, v in get_sorted(stats, time=t, type="residual_post_iteration", sortby="iter")]
+        ref = ref[~np.isnan(ref)]
+        assert len(hist) == len(ref)
+        # per-sweep residual histories agree to 1e-8 relative above the solver noise floor
+        np.testing.assert_allclose(hist, ref, rtol=1e-6, atol=2e-11 * max(1.0, float(g["uend_maxabs"])))
+    # error relative to the solution scale of the run (the initial value for strongly decaying solutions: the SDC
+    # residual tolerance that terminates every step is absolute)
+    scale = max(abs(u0), float(g["uend_maxabs"]))
+    if "uend" in g:
+        assert np.max(np.abs(uend.get() - g["uend"])) <= uend_tol * scale
+    assert abs(abs(uend) - float(g["uend_maxabs"])) <= uend_tol * scale
+    for key in P.work_counters:
+        got = [int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")]
+        want = g["work_" + key].tolist()
+        if key in ("newton", "rhs"):
+            assert got == want, (key, got, want)
+        else:
+            assert close_counts(got, want, count_slack), (key, got, want)
+    return dict(niter=niter, uend=uend, stats=stats)

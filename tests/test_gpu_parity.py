@@ -1,0 +1,200 @@
+"""GPU parity suite (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI of libsdcb200.so; the
+expected values are the golden fixtures of the unmodified reference and, for fresh seeded inputs, the CPU oracle.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def cuda_backend():
+    from pysdc_b200 import backend
+
+    old = backend._backend
+    backend.set_backend(backend.CudaBackend())
+    yield backend._backend
+    backend.set_backend(old)
+
+
+def test_device_is_blackwell(cuda_backend):
+    info = cuda_backend.device_info()
+    assert info["cc"][0] >= 10, info
+    assert info["solver_ctas"] >= info["sm_count"] > 0
+
+
+@pytest.mark.parametrize("name", golden_names("op_"))
+def test_operator(name):
+    pc.check_operator(name)
+
+
+@pytest.mark.parametrize("name", golden_names("sweep_"))
+def test_sweep_dump(name):
+    pc.check_sweep_dump(name)
+
+
+@pytest.mark.parametrize("name", golden_names("run_"))
+def test_run(name):
+    pc.check_run(name, count_slack=0.25 if "heat1d" in name else 0.02)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel-level checks on ragged / awkward shapes
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("count", [2, 30, 510, 4098, 1 << 20])
+def test_streaming_kernels(cuda_backend, count):
+    import torch
+
+    be = cuda_backend
+    rng = np.random.default_rng(count)
+    x, y = rng.standard_normal(count), rng.standard_normal(count)
+    tx, ty = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out = torch.empty_like(tx)
+    be.axpby(0.3, tx, -1.7, ty, out)
+    np.testing.assert_allclose(out.cpu().numpy(), 0.3 * x - 1.7 * y, rtol=0, atol=4e-16 * 3)
+    assert be.maxabs(tx) == float(np.max(np.abs(x)))
+    x[count // 2] = np.nan
+    assert np.isnan(be.maxabs(torch.from_numpy(x).cuda()))
+    # collocation: 3 outputs from 5 inputs, base and one optional add
+    ins = [rng.standard_normal(count) for _ in range(5)]
+    W = rng.standard_normal((3, 5))
+    base, add1 = rng.standard_normal(count), rng.standard_normal(count)
+    outs = [torch.empty(count, dtype=torch.float64, device="cuda") for _ in range(3)]
+    be.colloc_apply(W, [torch.from_numpy(v).cuda() for v in ins], torch.from_numpy(base).cuda(),
+                    [None, torch.from_numpy(add1).cuda(), None], outs)
+    for m in range(3):
+        want = sum(W[m, k] * ins[k] for k in range(5)) + base + (add1 if m == 1 else 0.0)
+        np.testing.assert_allclose(outs[m].cpu().numpy(), want, rtol=0, atol=1e-14)
+    us = [rng.standard_normal(count) for _ in range(3)]
+    norms = torch.zeros(3, dtype=torch.float64, device="cuda")
+    res = [torch.empty(count, dtype=torch.float64, device="cuda") for _ in range(3)]
+    be.colloc_residual(W, [torch.from_numpy(v).cuda() for v in ins], torch.from_numpy(base).cuda(),
+                       [torch.from_numpy(v).cuda() for v in us], None, res, norms)
+    for m in range(3):
+        want = sum(W[m, k] * ins[k] for k in range(5)) + (base - us[m])
+        np.testing.assert_allclose(res[m].cpu().numpy(), want, rtol=0, atol=1e-14)
+        assert abs(float(norms[m]) - np.max(np.abs(want))) < 1e-14
+
+
+@pytest.mark.parametrize("ndim,n,bc", [(1, 5, "dirichlet-zero"), (1, 1023, "dirichlet-zero"), (1, 6, "periodic"),
+                                        (1, 1000, "periodic"), (2, 3, "dirichlet-zero"), (2, 65, "dirichlet-zero"),
+                                        (2, 127, "dirichlet-zero"), (2, 4, "periodic"), (2, 66, "periodic"),
+                                        (2, 130, "periodic"), (3, 3, "dirichlet-zero"), (3, 33, "dirichlet-zero"),
+                                        (3, 65, "dirichlet-zero"), (3, 4, "periodic"), (3, 34, "periodic"),
+                                        (3, 66, "periodic")])
+def test_stencil_and_cg_against_oracle(oracle, ndim, n, bc):
+    """eval_f and solve_system on ragged tile shapes (sizes that do not fill the 64x8x32 tiles) vs the CPU oracle."""
+    from pysdc_b200.problems import heatNd_unforced
+
+    nvars = (n,) * ndim if ndim > 1 else n
+    freq = (2,) * ndim if ndim > 1 else 2
+    P = heatNd_unforced(nvars=nvars, nu=0.37, freq=freq, bc=bc, solver_type="CG", lintol=1e-12, liniter=500)
+    O = oracle.HeatFD(nvars=nvars, nu=0.37, freq=freq, bc=bc, solver_type="CG", lintol=1e-12, liniter=500)
+    rng = np.random.default_rng(100 * ndim + n)
+    u = rng.standard_normal(O.nvars)
+    rhs = rng.standard_normal(O.nvars)
+    f = P.eval_f(pc.to_mesh(P, u), 0.0).get()
+    f_ref = O.eval_f(u, 0.0)
+    assert np.max(np.abs(f - f_ref)) <= pc.stencil_tol(P, np.max(np.abs(u)), f_ref)
+    factor = 0.4 * O.dx_grid**2 / 0.37 * 8  # moderate condition number
+    sol = P.solve_system(pc.to_mesh(P, rhs), factor, pc.to_mesh(P, u), 0.0).get()
+    sol_ref = O.solve_system(rhs, factor, u, 0.0)
+    assert pc.relerr(sol, sol_ref) < pc.TOL_SOLVE
+    assert pc.close_counts(P.work_counters["CG"].niter, O.counters["CG"].niter)
+
+
+def test_batched_solve_equals_sequential():
+    """The node-batched launch must give each system exactly what a single-system launch gives (same reduction trees)."""
+    from pysdc_b200.problems import heatNd_unforced
+
+    P = heatNd_unforced(nvars=(33, 33, 33), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", solver_type="CG", lintol=1e-12)
+    rng = np.random.default_rng(5)
+    rhs = [pc.to_mesh(P, rng.standard_normal(P.nvars)) for _ in range(4)]
+    factors = [1e-4, 5e-4, 2e-3, 1e-2]  # very different iteration counts -> per-system convergence masks
+    xb = [pc.to_mesh(P, np.zeros(P.nvars)) for _ in range(4)]
+    P.solve_system_batch(rhs, factors, xb)
+    its_batched = P.work_counters["CG"].niter
+    for i in range(4):
+        xs = P.solve_system(rhs[i], factors[i], pc.to_mesh(P, np.zeros(P.nvars)), 0.0)
+        assert np.array_equal(xs.get(), xb[i].get()), i
+    assert P.work_counters["CG"].niter == 2 * its_batched
+
+
+def test_cg_edge_cases():
+    from pysdc_b200.problems import heatNd_unforced
+
+    P = heatNd_unforced(nvars=(31, 31), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-12, liniter=7)
+    zero = pc.to_mesh(P, np.zeros(P.nvars))
+    u = pc.to_mesh(P, np.random.default_rng(1).standard_normal(P.nvars))
+    # zero right-hand side: scipy returns b itself, no iterations
+    sol = P.solve_system(zero, 0.01, u, 0.0)
+    assert abs(sol) == 0.0 and P.work_counters["CG"].niter == 0
+    # iteration budget exhausted: current iterate is returned after exactly liniter iterations
+    sol = P.solve_system(u, 10.0, zero, 0.0)
+    assert P.work_counters["CG"].niter == 7 and np.isfinite(abs(sol))
+    # exact initial guess: converged before the first iteration
+    P2 = heatNd_unforced(nvars=(31, 31), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-10)
+    x = P2.solve_system(u, 0.01, zero, 0.0)
+    n0 = P2.work_counters["CG"].niter
+    x2 = P2.solve_system(u, 0.01, x, 0.0)
+    assert P2.work_counters["CG"].niter == n0 and np.array_equal(x2.get(), x.get())
+
+
+def test_datatype_surface():
+    """mesh / imex_mesh behave like the reference datatypes (tests/tests_core.py:19-60, test_multicomponent_mesh.py)."""
+    from pysdc_b200.datatypes import imex_mesh, mesh
+
+    init = ((15, 15), None, np.dtype("float64"))
+    a, b = mesh(init, val=1.0), mesh(init, val=2.5)
+    c = a + b
+    assert type(c) is mesh and abs(c) == 3.5 and abs(a - b) == 1.5 and abs(0.5 * b) == 1.25 and abs(b * 2) == 5.0
+    assert isinstance(abs(c), float)
+    d = mesh(c)
+    d[:] = 7.0
+    assert abs(c) == 3.5 and abs(d) == 7.0  # deep copy
+    a += b
+    assert abs(a) == 3.5
+    arr = np.arange(225, dtype=float).reshape(15, 15)
+    a[:] = arr
+    assert np.array_equal(a.get(), arr) and np.array_equal(np.asarray(a), arr)
+    assert np.array_equal(a.flatten().cpu().numpy(), arr.ravel())
+    assert abs(np.float64(2.0) * a) == 448.0
+    f = imex_mesh(init)
+    assert f.shape == (2, 15, 15) and type(f.impl) is mesh and f.expl.shape == (15, 15)
+    f.impl[:] = arr
+    f.expl[:] = -arr
+    assert np.array_equal(f.get()[0], arr) and np.array_equal(f.get()[1], -arr)
+    g = f + f
+    assert type(g) is imex_mesh and np.array_equal(g.get()[1], -2 * arr)
+    with pytest.raises(AttributeError):
+        f.nope
+    # the walls of the layout stay zero under arithmetic (they are the Dirichlet boundary)
+    assert float(a.vol.sum()) == float(arr.sum())
+
+
+def test_allencahn_newton_against_oracle(oracle):
+    from pysdc_b200.problems import allencahn_fullyimplicit
+
+    pp = dict(nvars=(64, 64), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9, lin_tol=1e-10, lin_maxiter=100,
+              radius=0.25)
+    P, O = allencahn_fullyimplicit(**pp), oracle.AllenCahnFD(**pp)
+    u0 = O.u_exact(0.0)
+    assert np.array_equal(P.u_exact(0.0).get(), u0)
+    rhs = u0 + 1e-3 * O.eval_f(u0, 0.0)
+    sol = P.solve_system(pc.to_mesh(P, rhs), 2e-3, pc.to_mesh(P, u0), 0.0).get()
+    sol_ref = O.solve_system(rhs, 2e-3, u0, 0.0)
+    assert pc.relerr(sol, sol_ref) < pc.TOL_SOLVE
+    assert P.work_counters["newton"].niter == O.counters["newton"].niter
+    assert pc.close_counts(P.work_counters["linear"].niter, O.counters["linear"].niter)
+
+
+def test_midsize_3d_run_against_oracle(oracle):
+    """Config 3 at 63^3 with the bench settings (restol=-1, K=4 sweeps): residual history and solution vs the fixture of
+    the reference and the oracle run on this host."""
+    out = pc.check_run("run_heat3d_gi_minsrns_63_K4")
+    spec, _ = load_golden("run_heat3d_gi_minsrns_63_K4")
+    ref = oracle.run_sdc(spec)
+    assert pc.relerr(out["uend"].get(), ref["uend"]) < pc.TOL_SOLVE
