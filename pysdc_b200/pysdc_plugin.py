@@ -1,0 +1,23 @@
+"""Drop-in classes for an unmodified pySDC installation.
+
+    from pysdc_b200.pysdc_plugin import heatNd_unforced, generic_implicit     # instead of pySDC.implementations...
+    description = {'problem_class': heatNd_unforced, 'sweeper_class': generic_implicit, ...}   # everything else as is
+    controller_nonMPI(num_procs=1, controller_params=..., description=description).run(u0, t0, Tend)
+
+The numerical mix-ins of ``sweepers.py`` / ``problems.py`` are bound to pySDC's OWN base classes
+(``pySDC.core.sweeper.Sweeper``, ``pySDC.core.problem.Problem``), so collocation and QDelta coefficients come from
+pySDC / qmat, ``Level`` and ``Step`` type checks pass (core/sweeper.py:253-256), and pySDC's controllers, hooks and
+convergence controllers run around them unchanged.  Importing this module needs pySDC (and its qmat dependency).
+"""
+from pySDC.core.problem import Problem as _PySDCProblem
+from pySDC.core.sweeper import Sweeper as _PySDCSweeper
+
+from . import problems as _problems
+from . import sweepers as _sweepers
+from .datatypes import imex_mesh, mesh  # noqa: F401
+
+globals().update({k: v for k, v in _problems._bind(_PySDCProblem).items()})
+globals().update({k: v for k, v in _sweepers._bind(_PySDCSweeper).items()})
+
+__all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "generic_implicit",
+           "imex_1st_order"]

@@ -33,4 +33,4 @@ def test_sweep_dump(name):
 def test_run(name):
     # 1-D grids are badly conditioned (kappa ~ 1e4): CG loses orthogonality and its iteration count depends on
     # rounding details at the 10 % level; SDC iteration counts and the solution are unaffected
-    pc.check_run(name, count_slack=0.25 if "heat1d" in name else 0.02)
+    pc.check_run(name, count_slack=None if "heat1d" in name else 0.02)

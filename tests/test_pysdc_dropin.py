@@ -1,0 +1,65 @@
+"""Drop-in check inside the UNMODIFIED reference (build container only: needs /root/reference): pySDC's own
+controller_nonMPI, Step, Level, hooks and convergence controllers drive the classes of pysdc_b200.pysdc_plugin selected
+purely through the description dict.  The kernel library is replaced by the numpy test double (no GPU here); the GPU
+suite runs the same sweepers / problems against the real kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+REF = os.environ.get("PYSDC_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pySDC")), reason="reference tree not present")
+
+
+@pytest.fixture()
+def plugin():
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "qmat_shim"))
+    sys.path.insert(0, REF)
+    from fake_backend import NumpyBackend
+    from pysdc_b200 import backend
+
+    old = backend._backend
+    backend.set_backend(NumpyBackend())
+    from pysdc_b200 import pysdc_plugin
+
+    yield pysdc_plugin
+    backend.set_backend(old)
+
+
+@pytest.mark.parametrize("name", ["run_heat3d_gi_minsrns_31", "run_heat3d_gi_lu_31", "run_heat2d_imex_lu_63",
+                                  "run_heat1d_imex_ie_step3A", "run_allencahn_gi_lu_64", "run_heat3d_gi_minsrflex_31"])
+def test_reference_controller_drives_plugin_classes(plugin, name):
+    from pySDC.core.sweeper import Sweeper
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+    from pySDC.implementations.hooks.log_work import LogWork
+
+    spec, g = load_golden(name)
+    pp = dict(spec["problem_params"])
+    for k in ("nvars", "freq"):
+        if isinstance(pp.get(k), list):
+            pp[k] = tuple(pp[k])
+    description = dict(problem_class=getattr(plugin, spec["problem"]), problem_params=pp,
+                       sweeper_class=getattr(plugin, spec["sweeper"]), sweeper_params=dict(spec["sweeper_params"]),
+                       level_params=dict(spec["level_params"]), step_params=dict(spec["step_params"]))
+    c = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40, "hook_class": [LogWork]},
+                          description=description)
+    L = c.MS[0].levels[0]
+    assert isinstance(L.sweep, Sweeper)
+    P = L.prob
+    if spec["u0"] == "exact":
+        u0 = P.u_exact(spec["t0"])
+    else:
+        u0 = P.u_init
+        u0[:] = np.random.default_rng(spec["seed"]).standard_normal(P.nvars)
+    uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+    niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
+    assert niter == g["niter"].tolist()
+    assert np.max(np.abs(uend.get() - g["uend"])) <= 1e-10 * max(abs(u0), float(g["uend_maxabs"]))
+    for key in P.work_counters:
+        got = [int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")]
+        want = g["work_" + key].tolist()
+        assert np.all(np.abs(np.array(got) - np.array(want)) <= np.maximum(np.ceil(0.02 * np.array(want)), 1)), (key, got, want)
