@@ -5,106 +5,29 @@
 // flow stays uniform), the per-system convergence tests and the iteration counters live on the device; the host
 // never synchronises inside a solve.  Grid = (co-resident CTAs per SM) x (SM count), software grid barrier
 // (release/acquire at gpu scope).  The recurrence follows scipy.sparse.linalg.cg (scipy 1.18.1, _isolve/iterative.py)
-// statement by statement, including the unfused rounding of  p*=beta; p+=r;  x+=alpha*p;  r-=alpha*q.
-#include "stencil.cuh"
+// statement by statement, including the unfused rounding of  p*=beta; p+=r;  x+=alpha*p;  r-=alpha*q, but is
+// scheduled as two fused passes per iteration (see cg_collective).
+#include "cg_common.cuh"
 
 namespace sdcb200 {
 namespace {
 
-struct Sys {
-    const double* b;     // right-hand side
-    double* x;           // in: initial guess, out: solution
-    double* r;
-    double* p;
-    double* q;
-    const double* dvec;  // optional full diagonal of the operator (Allen-Cahn Jacobian); NULL -> m_diag
-    double m_diag;       // 1 - factor*a_diag
-    double m_off;        // -factor*a_off
-};
-
-struct CgArgs {
-    Geom g;
-    int B;
-    Sys s[SDCB200_MAX_NODES];
-    double rtol;
-    int maxiter;
-    double* partials;  // [2][MAX_NODES][gridDim.x]
-    unsigned* bar;     // grid barrier word (zero before the launch)
-    int* iters_out;    // [B], += iterations
-};
-
-struct NewtonArgs {
-    Geom g;
-    double factor, a_diag, a_off, inv_eps2;
-    int nu_exp;
-    const double* rhs;
-    double* u;
-    double* gvec;  // Newton residual
-    double* z;     // Newton update (CG solution)
-    double* dvec;  // Jacobian diagonal
-    double* r;
-    double* p;
-    double* q;
-    double newton_tol, lin_tol, inexact_ratio;
-    int newton_maxiter, lin_maxiter;
-    double* partials;
-    unsigned* bar;
-    int* counters_out;  // [0] += newton iterations, [1] += CG iterations
-};
-
 // ---------------------------------------------------------------------------------------------------------------------
-// grid-wide barrier (all CTAs co-resident: cooperative launch).  Same protocol as cooperative groups' grid sync:
-// CTA barrier, one thread arrives with a gpu-scope release and spins with gpu-scope acquire, CTA barrier.  CTA 0 adds
-// the complement so that the top bit flips once per generation and the word never needs resetting.
-// ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned add = (blockIdx.x == 0) ? (0x80000000u - (gridDim.x - 1)) : 1u;
-        unsigned old;
-        asm volatile("atom.add.release.gpu.u32 %0,[%1],%2;" : "=r"(old) : "l"(bar), "r"(add) : "memory");
-        unsigned cur;
-        do {
-            asm volatile("ld.acquire.gpu.u32 %0,[%1];" : "=r"(cur) : "l"(bar) : "memory");
-        } while (((old ^ cur) & 0x80000000u) == 0);
-    }
-    __syncthreads();
-}
-
-// Sum the per-CTA partials of one quantity in a fixed order; identical bits in every thread of every CTA.
-__device__ __forceinline__ double grid_sum(const double* partials, int slot, int b, double* scratch) {
-    const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
-    double v = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(src + i);
-    return block_sum(v, scratch);
-}
-__device__ __forceinline__ double grid_max(const double* partials, int slot, int b, double* scratch) {
-    const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
-    double v = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v = fmax(v, __ldcg(src + i));
-    return block_max(v, scratch);
-}
-__device__ __forceinline__ void put_partial(double* partials, int slot, int b, double v) {
-    if (threadIdx.x == 0) partials[(size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x + blockIdx.x] = v;
-}
-
-// scalar state of the solver, one copy per CTA in shared memory, written by thread 0 only
-struct CgShared {
-    double scratch[33];
-    double bb[SDCB200_MAX_NODES], rr[SDCB200_MAX_NODES], rho_prev[SDCB200_MAX_NODES];
-    double alpha[SDCB200_MAX_NODES], beta[SDCB200_MAX_NODES];
-    int iters[SDCB200_MAX_NODES];
-    unsigned active;  // bit b set: system b still iterating
-};
-
-// ---------------------------------------------------------------------------------------------------------------------
-// the collective CG routine: every thread of the grid calls it with identical arguments
+// the collective CG routine: every thread of the grid calls it with identical arguments.
+//
+// Two grid-wide phases per iteration, 8 field streams per system and iteration (a textbook CG moves 11):
+//   phase A   p <- r + beta p_old   evaluated on the fly on every stencil point (tile + halo) from r and p_old, so the
+//             direction update and the operator application share one pass:  reads r, p_old;  writes p;  p.(M p)
+//             p is double-buffered (S.p / S.q alternate) because neighbouring tiles still read p_old's halo.
+//   phase B   M p is evaluated again by the stencil (p is final now) instead of being stored and re-read:
+//             r <- r - alpha M p,  x <- x + alpha p,  r.r :  reads p, r, x;  writes r, x.
+// Rounding follows scipy:  p = fl(fl(p*beta) + r),  x = fl(x + fl(alpha*p)),  r = fl(r - fl(alpha*q)).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NDIM, bool PER>
 __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, int maxiter, double* partials,
                               unsigned* bar, CgShared& sh) {
-    const Units U = make_units(g);
-    const long long n2 = g.vol / 2;
+    const Units U = make_units(g, (int)gridDim.x);
+    const long long n2 = g.owned / 2;
     const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
     const long long gstride = (long long)gridDim.x * kThreads;
 
@@ -175,42 +98,29 @@ __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, i
         __syncthreads();
         const unsigned act = sh.active;
         if (act == 0) break;
+        // all systems start together, so the parity of `it` tells which buffer holds p_old for every active one
+        const int cur = it & 1;
 
-        // ---- p = r + beta p ---------------------------------------------------------------------------------------------
+        // ---- phase A: p = r + beta p_old on the fly, q = M p, p.q --------------------------------------------------------
         for (int b = 0; b < B; ++b) {
             if (!(act >> b & 1u)) continue;
             const Sys& S = s[b];
-            const double beta = sh.beta[b];
-            if (it == 0) {
-                for (long long i = gtid; i < n2; i += gstride) st2(S.p + 2 * i, ld2(S.r + 2 * i));
-            } else {
-                for (long long i = gtid; i < n2; i += gstride) {
-                    const double2 r = ld2(S.r + 2 * i);
-                    double2 p = ld2(S.p + 2 * i);
-                    p.x = __dadd_rn(__dmul_rn(p.x, beta), r.x);
-                    p.y = __dadd_rn(__dmul_rn(p.y, beta), r.y);
-                    st2(S.p + 2 * i, p);
-                }
-            }
-        }
-        grid_barrier(bar);
-
-        // ---- q = M p, p.q -----------------------------------------------------------------------------------------------
-        for (int b = 0; b < B; ++b) {
-            if (!(act >> b & 1u)) continue;
-            const Sys& S = s[b];
+            double* p_new = cur ? S.q : S.p;
+            const DirectionLoader dir{S.r, it == 0 ? nullptr : (cur ? S.p : S.q), sh.beta[b]};
             double pq = 0.0;
             for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
-                stencil_unit<NDIM, PER>(g, U, S.p, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
-                    double2 d = make_double2(S.m_diag, S.m_diag);
-                    if (S.dvec != nullptr) d = ld2(S.dvec + idx);
-                    double2 q;
-                    q.x = v0 ? fma(S.m_off, nb.x, d.x * c.x) : 0.0;
-                    q.y = v1 ? fma(S.m_off, nb.y, d.y * c.y) : 0.0;
-                    st2(S.q + idx, q);
-                    pq = fma(c.x, q.x, pq);
-                    pq = fma(c.y, q.y, pq);
-                });
+                stencil_unit_ld<NDIM, PER>(
+                    g, U, dir, unit,
+                    [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                        st2(p_new + idx, c);  // walls: r = p_old = 0 there, so c is an exact zero
+                        double2 d = make_double2(S.m_diag, S.m_diag);
+                        if (S.dvec != nullptr) d = ld2(S.dvec + idx);
+                        const double qx = v0 ? fma(S.m_off, nb.x, d.x * c.x) : 0.0;
+                        const double qy = v1 ? fma(S.m_off, nb.y, d.y * c.y) : 0.0;
+                        pq = fma(c.x, qx, pq);
+                        pq = fma(c.y, qy, pq);
+                    },
+                    [&](long long idx, double2 c) { st2(p_new + idx, c); });
             }
             pq = block_sum(pq, sh.scratch);
             put_partial(partials, 0, b, pq);
@@ -223,23 +133,27 @@ __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, i
         }
         __syncthreads();
 
-        // ---- x += alpha p, r -= alpha q, r.r ----------------------------------------------------------------------------
+        // ---- phase B: r -= alpha M p, x += alpha p, r.r ---------------------------------------------------------------
         for (int b = 0; b < B; ++b) {
             if (!(act >> b & 1u)) continue;
             const Sys& S = s[b];
+            const double* p = cur ? S.q : S.p;
             const double alpha = sh.alpha[b];
             double rr = 0.0;
-            for (long long i = gtid; i < n2; i += gstride) {
-                const double2 p = ld2(S.p + 2 * i), q = ld2(S.q + 2 * i);
-                double2 x = ld2(S.x + 2 * i), r = ld2(S.r + 2 * i);
-                x.x = __dadd_rn(x.x, __dmul_rn(alpha, p.x));
-                x.y = __dadd_rn(x.y, __dmul_rn(alpha, p.y));
-                r.x = __dsub_rn(r.x, __dmul_rn(alpha, q.x));
-                r.y = __dsub_rn(r.y, __dmul_rn(alpha, q.y));
-                st2(S.x + 2 * i, x);
-                st2(S.r + 2 * i, r);
-                rr = fma(r.x, r.x, rr);
-                rr = fma(r.y, r.y, rr);
+            for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+                stencil_unit<NDIM, PER>(g, U, p, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                    double2 d = make_double2(S.m_diag, S.m_diag);
+                    if (S.dvec != nullptr) d = ld2(S.dvec + idx);
+                    double2 r = ld2(S.r + idx), x = ld2(S.x + idx);
+                    r.x = v0 ? __dsub_rn(r.x, __dmul_rn(alpha, fma(S.m_off, nb.x, d.x * c.x))) : 0.0;
+                    r.y = v1 ? __dsub_rn(r.y, __dmul_rn(alpha, fma(S.m_off, nb.y, d.y * c.y))) : 0.0;
+                    x.x = __dadd_rn(x.x, __dmul_rn(alpha, c.x));
+                    x.y = __dadd_rn(x.y, __dmul_rn(alpha, c.y));
+                    st2(S.r + idx, r);
+                    st2(S.x + idx, x);
+                    rr = fma(r.x, r.x, rr);
+                    rr = fma(r.y, r.y, rr);
+                });
             }
             rr = block_sum(rr, sh.scratch);
             put_partial(partials, 1, b, rr);

@@ -36,9 +36,12 @@ struct Geom {
     int n;          // points per dimension
     int P;          // pitch = n + (n & 1)
     int periodic;   // 0 dirichlet-zero (walls), 1 periodic
+    int nz;         // 3-D: planes owned along the slowest axis (= n unless the grid is slab-decomposed)
+    int zhalo;      // 3-D slabs: planes -1 and nz are halo planes filled by the neighbours (no wrap in z)
     long long sy;   // stride of y = P
     long long sz;   // stride of z = P*P
-    long long vol;  // P^ndim
+    long long vol;  // doubles of one field (without the guard)
+    long long owned;  // doubles spanning the owned planes (streaming loops)
 };
 
 inline Geom make_geom(int ndim, int n, int bc) {
@@ -51,6 +54,19 @@ inline Geom make_geom(int ndim, int n, int bc) {
     g.sz = (long long)g.P * g.P;
     g.vol = g.P;
     for (int d = 1; d < ndim; ++d) g.vol *= g.P;
+    g.nz = ndim == 3 ? n : 1;
+    g.zhalo = 0;
+    g.owned = ndim == 3 ? g.sz * g.nz : g.vol;
+    return g;
+}
+
+// slab of a 3-D grid: nz owned planes of an n x n cross-section, halo planes at -1 (the guard) and nz
+inline Geom make_slab_geom(int n, int nz, int bc) {
+    Geom g = make_geom(3, n, bc);
+    g.nz = nz;
+    g.zhalo = 1;
+    g.vol = g.sz * (nz + 1);
+    g.owned = g.sz * nz;
     return g;
 }
 

@@ -1,12 +1,16 @@
 // Matrix-free order-2 Laplacian stencil on the walled layout (include/sdc_b200.h), shared by eval_f, the CG
 // operator application and the Newton residual.
 //
-// Work decomposition: a "unit" is a tile of 64(x) x 8(y) points [x ZC planes in 3-D, marched in z with the centre
+// Work decomposition: a "unit" is a tile of 64(x) x 8(y) points [x chunk_z planes in 3-D, marched in z with the centre
 // column held in registers]; 1-D grids use 512-point segments.  One CTA (256 threads = 8 warps, one warp per tile
 // row, one double2 per lane) processes a unit; x-neighbours come from warp shuffles, y-neighbours from L1/L2 (rows of
 // the same tile are loaded by the neighbouring warps of the same CTA), z-neighbours from registers.  On Dirichlet
 // grids every neighbour access is in-bounds and reads an exact zero at the boundary (walls / guard), so the inner
 // loop has no boundary branches; periodic grids wrap indices explicitly.
+//
+// The field the stencil is applied to is described by a LOADER (pair(idx) -> double2, one(idx) -> double): a plain
+// array, or an expression of several arrays evaluated on the fly (the CG search direction  r + beta*p_old, see cg.cu),
+// which is what lets the direction update and the operator application share one pass over memory.
 #pragma once
 #include "common.cuh"
 
@@ -14,16 +18,19 @@ namespace sdcb200 {
 
 constexpr int kTileX = 64;   // doubles per tile row (32 lanes x double2)
 constexpr int kTileY = 8;    // rows per tile (one per warp)
-constexpr int kChunkZ = 32;  // planes marched per unit in 3-D
 constexpr int kSeg1D = 2 * kThreads;
 
 struct Units {
     int nxt, nyt, nzc;
+    int chunk_z;  // planes marched per unit in 3-D
     int per_field;
 };
 
-__host__ __device__ inline Units make_units(const Geom& g) {
+// `target_ctas` > 0: choose the z-chunk so that the units of one field fill whole waves of a persistent grid of that
+// many CTAs with the longest possible march (fewer re-read halo planes); 0: fixed 32-plane chunks.
+__host__ __device__ inline Units make_units(const Geom& g, int target_ctas = 0) {
     Units u;
+    u.chunk_z = 1;
     if (g.ndim == 1) {
         u.nxt = (g.P + kSeg1D - 1) / kSeg1D;
         u.nyt = 1;
@@ -31,17 +38,71 @@ __host__ __device__ inline Units make_units(const Geom& g) {
     } else {
         u.nxt = (g.P + kTileX - 1) / kTileX;
         u.nyt = (g.n + kTileY - 1) / kTileY;
-        u.nzc = g.ndim == 3 ? (g.n + kChunkZ - 1) / kChunkZ : 1;
+        u.nzc = 1;
+        if (g.ndim == 3) {
+            const int nz = g.nz;
+            int chunk = 32;
+            if (target_ctas > 0) {
+                // candidates 128, 64, 32, 16: take the longest march that still leaves >= 4 rounds of units per CTA
+                // and wastes < 8 % of the last round
+                const int tiles = u.nxt * u.nyt;
+                chunk = 16;
+                for (int c = 128; c >= 16; c >>= 1) {
+                    const long long units = (long long)tiles * ((nz + c - 1) / c);
+                    const long long rounds = (units + target_ctas - 1) / target_ctas;
+                    if (rounds >= 4 && (double)units / (double)(rounds * target_ctas) > 0.92) {
+                        chunk = c;
+                        break;
+                    }
+                }
+            }
+            u.chunk_z = chunk;
+            u.nzc = (nz + chunk - 1) / chunk;
+        }
     }
     u.per_field = u.nxt * u.nyt * u.nzc;
     return u;
 }
 
+// ---- loaders ---------------------------------------------------------------------------------------------------------
+struct PlainLoader {
+    const double* u;
+    __device__ __forceinline__ double2 pair(long long idx) const { return ld2(u + idx); }
+    __device__ __forceinline__ double one(long long idx) const { return u[idx]; }
+};
+
+// search direction of CG evaluated on the fly:  r + beta * p_old  with the rounding of scipy's  `p *= beta; p += r`
+// (p_old == nullptr: first iteration, p = r)
+struct DirectionLoader {
+    const double* r;
+    const double* p_old;
+    double beta;
+    __device__ __forceinline__ double2 pair(long long idx) const {
+        const double2 rv = ld2(r + idx);
+        if (p_old == nullptr) return rv;
+        const double2 pv = ld2(p_old + idx);
+        return make_double2(__dadd_rn(__dmul_rn(pv.x, beta), rv.x), __dadd_rn(__dmul_rn(pv.y, beta), rv.y));
+    }
+    __device__ __forceinline__ double one(long long idx) const {
+        const double rv = r[idx];
+        if (p_old == nullptr) return rv;
+        return __dadd_rn(__dmul_rn(p_old[idx], beta), rv);
+    }
+};
+
+struct NoHalo {
+    __device__ __forceinline__ void operator()(long long, double2) const {}
+};
+
 // Visit every grid point of one unit.  f(idx, c, nb, v0, v1): idx = flat index of the pair (x, x+1), c = centre
 // values, nb = sum of the 2*NDIM neighbours of each, v0/v1 = whether x / x+1 are grid points (false on the wall).
-// `u` must not be written by anybody while the phase that calls this runs.
-template <int NDIM, bool PER, class F>
-__device__ __forceinline__ void stencil_unit(const Geom& g, const Units& U, const double* u, int unit, F&& f) {
+// The arrays behind `ld` must not be written by anybody while the phase that calls this runs.
+// 3-D slabs (g.zhalo): planes -1 and nz hold the neighbouring slab's boundary planes (or zeros at the domain
+// boundary); h(idx, c) is called with the loader's value on those two planes for the units that touch them, so that
+// an on-the-fly field can be materialised there as well.
+template <int NDIM, bool PER, class L, class F, class H = NoHalo>
+__device__ __forceinline__ void stencil_unit_ld(const Geom& g, const Units& U, const L& ld, int unit, F&& f,
+                                                H&& h = H()) {
     const int lane = threadIdx.x & 31;
     const int n = g.n, P = g.P;
     int x, y = 0, z0 = 0, z1 = 1;
@@ -54,8 +115,8 @@ __device__ __forceinline__ void stencil_unit(const Geom& g, const Units& U, cons
         y = ty * kTileY + (threadIdx.x >> 5);
         if constexpr (NDIM == 3) {
             const int tz = unit / (U.nxt * U.nyt);
-            z0 = tz * kChunkZ;
-            z1 = min(z0 + kChunkZ, n);
+            z0 = tz * U.chunk_z;
+            z1 = min(z0 + U.chunk_z, g.nz);
         }
         if (y >= n) return;  // warp-uniform: whole warp owns a row outside the grid
     }
@@ -71,39 +132,37 @@ __device__ __forceinline__ void stencil_unit(const Geom& g, const Units& U, cons
     }
     const bool need_left = (lane == 0);
     const bool need_right = (lane == 31) || (x + 2 >= P);
+    const bool zwrap = PER && NDIM == 3 && !g.zhalo;
 
     long long idx = row + xs + (NDIM == 3 ? (long long)z0 * g.sz : 0);
     double2 c_prev = make_double2(0.0, 0.0), c_next = make_double2(0.0, 0.0);
-    double2 c = ld2(u + idx);
+    double2 c = ld.pair(idx);
     if constexpr (NDIM == 3) {
         long long below = -g.sz;
-        if constexpr (PER) {
-            if (z0 == 0) below = (long long)(n - 1) * g.sz;
-        }
-        c_prev = ld2(u + idx + below);
+        if (zwrap && z0 == 0) below = (long long)(g.nz - 1) * g.sz;
+        c_prev = ld.pair(idx + below);
+        if (g.zhalo && z0 == 0 && inx) h(idx + below, c_prev);
     }
     for (int z = z0; z < z1; ++z) {
         if constexpr (NDIM == 3) {
             long long above = g.sz;
-            if constexpr (PER) {
-                if (z == n - 1) above = -(long long)(n - 1) * g.sz;
-            }
-            c_next = ld2(u + idx + above);
+            if (zwrap && z == g.nz - 1) above = -(long long)(g.nz - 1) * g.sz;
+            c_next = ld.pair(idx + above);
         }
         // x direction: shuffles inside the warp, two edge lanes load from the neighbouring tile / wrap around
         double left = __shfl_up_sync(0xffffffffu, c.y, 1);
         double right = __shfl_down_sync(0xffffffffu, c.x, 1);
         if (need_left) {
-            if (PER && x == 0) left = u[idx + (n - 1)];
-            else left = u[idx - 1];  // Dirichlet x == 0: previous row's wall (or the guard) = 0
+            if (PER && x == 0) left = ld.one(idx + (n - 1));
+            else left = ld.one(idx - 1);  // Dirichlet x == 0: previous row's wall (or the guard) = 0
         }
         if (need_right) {
-            if (x + 2 < P) right = u[idx + 2];
-            else right = PER ? u[idx - xs] : 0.0;  // wrap to x = 0 / beyond the wall
+            if (x + 2 < P) right = ld.one(idx + 2);
+            else right = PER ? ld.one(idx - xs) : 0.0;  // wrap to x = 0 / beyond the wall
         }
         double2 nb = make_double2(left + c.y, c.x + right);
         if constexpr (NDIM >= 2) {
-            const double2 a = ld2(u + idx + up), b = ld2(u + idx + dn);
+            const double2 a = ld.pair(idx + up), b = ld.pair(idx + dn);
             nb.x += a.x + b.x;
             nb.y += a.y + b.y;
         }
@@ -118,6 +177,15 @@ __device__ __forceinline__ void stencil_unit(const Geom& g, const Units& U, cons
             idx += g.sz;
         }
     }
+    if constexpr (NDIM == 3) {
+        if (g.zhalo && z1 == g.nz && inx) h(idx, c);  // c now holds plane nz
+    }
+}
+
+// plain-array convenience overload
+template <int NDIM, bool PER, class F>
+__device__ __forceinline__ void stencil_unit(const Geom& g, const Units& U, const double* u, int unit, F&& f) {
+    stencil_unit_ld<NDIM, PER>(g, U, PlainLoader{u}, unit, static_cast<F&&>(f));
 }
 
 }  // namespace sdcb200
