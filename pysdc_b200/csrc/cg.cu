@@ -8,6 +8,7 @@
 // statement by statement, including the unfused rounding of  p*=beta; p+=r;  x+=alpha*p;  r-=alpha*q, but is
 // scheduled as two fused passes per iteration (see cg_collective).
 #include "cg_common.cuh"
+#include "cg_pipe.cuh"
 
 namespace sdcb200 {
 namespace {
@@ -180,6 +181,137 @@ __global__ void __launch_bounds__(kThreads) cg_kernel(const __grid_constant__ Cg
         for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// the same solver with both passes of the iteration running as bulk-async pipelines (cg_pipe.cuh): 2-D / 3-D
+// Dirichlet grids with a constant diagonal, i.e. the heat-equation node solves.  Launched with kPipeThreads threads
+// (8 consumer warps + 1 producer warp); the set-up pass uses the register-marching stencil on the first 8 warps.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NDIM>
+__device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const PipeMaps& maps, double rtol, int maxiter,
+                                   double* partials, unsigned* bar, CgShared& sh, PipeSmem& sm) {
+    const Units U = make_units(g, (int)gridDim.x);
+    const PUnits PU = make_punits(g, 1, (int)gridDim.x);
+    const long long n2 = g.owned / 2;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    unsigned kstep = 0;
+
+    // ---- r = b - M x0, ||b||^2, ||r||^2 ------------------------------------------------------------------------------
+    for (int b = 0; b < B; ++b) {
+        const Sys& S = s[b];
+        double bb = 0.0, rr = 0.0;
+        if (threadIdx.x < kThreads) {
+            for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+                stencil_unit<NDIM, false>(g, U, S.x, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                    const double2 rhs = ld2(S.b + idx);
+                    double2 r;
+                    r.x = v0 ? rhs.x - fma(S.m_off, nb.x, S.m_diag * c.x) : 0.0;
+                    r.y = v1 ? rhs.y - fma(S.m_off, nb.y, S.m_diag * c.y) : 0.0;
+                    st2(S.r + idx, r);
+                    if (v0) bb = fma(rhs.x, rhs.x, bb);
+                    if (v1) bb = fma(rhs.y, rhs.y, bb);
+                    rr = fma(r.x, r.x, rr);
+                    rr = fma(r.y, r.y, rr);
+                });
+            }
+        }
+        bb = block_sum(bb, sh.scratch);
+        rr = block_sum(rr, sh.scratch);
+        put_partial(partials, 0, b, bb);
+        put_partial(partials, 1, b, rr);
+    }
+    fence_proxy_async_global();
+    grid_barrier(bar);
+    for (int b = 0; b < B; ++b) {
+        const double bb = grid_sum(partials, 0, b, sh.scratch);
+        const double rr = grid_sum(partials, 1, b, sh.scratch);
+        if (threadIdx.x == 0) {
+            sh.bb[b] = bb;
+            sh.rr[b] = rr;
+            sh.iters[b] = 0;
+            sh.rho_prev[b] = 1.0;
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned act = 0;
+        for (int b = 0; b < B; ++b)
+            if (sh.bb[b] != 0.0) act |= 1u << b;
+        sh.active = act;
+    }
+    __syncthreads();
+    for (int b = 0; b < B; ++b) {
+        if (sh.bb[b] == 0.0) {
+            for (long long i = gtid; i < n2; i += gstride) st2(s[b].x + 2 * i, make_double2(0.0, 0.0));
+        }
+    }
+
+    for (int it = 0;; ++it) {
+        if (threadIdx.x == 0) {
+            unsigned act = sh.active;
+            int na = 0;
+            for (int b = 0; b < B; ++b) {
+                if (!(act >> b & 1u)) continue;
+                const double atol = rtol * sqrt(sh.bb[b]);
+                if (sqrt(sh.rr[b]) < atol || it >= maxiter) {
+                    act &= ~(1u << b);
+                } else {
+                    sh.beta[b] = it > 0 ? sh.rr[b] / sh.rho_prev[b] : 0.0;
+                    sm.act_list[na++] = b;
+                }
+            }
+            sh.active = act;
+            sm.nact = na;
+        }
+        __syncthreads();
+        const unsigned act = sh.active;
+        if (act == 0) break;
+        const int cur = it & 1;  // p_new goes to (cur ? S.q : S.p), p_old is the other buffer
+
+        fence_proxy_async_global();
+        pipe_phase_a<NDIM>(g, PU, s, maps, it == 0, cur, sh, sm, partials, kstep);
+        fence_proxy_async_global();
+        grid_barrier(bar);
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const double pq = grid_sum(partials, 0, b, sh.scratch);
+            if (threadIdx.x == 0) sh.alpha[b] = sh.rr[b] / pq;
+        }
+        __syncthreads();
+
+        fence_proxy_async_global();
+        pipe_phase_b<NDIM>(g, PU, s, maps, cur, sh, sm, partials, kstep);
+        fence_proxy_async_global();
+        grid_barrier(bar);
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const double rr = grid_sum(partials, 1, b, sh.scratch);
+            if (threadIdx.x == 0) {
+                sh.rho_prev[b] = sh.rr[b];
+                sh.rr[b] = rr;
+                sh.iters[b] += 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+struct PipeArgs {
+    CgArgs cg;
+    PipeMaps maps;
+};
+
+template <int NDIM>
+__global__ void __launch_bounds__(kPipeThreads, 2) cg_pipe_kernel(const __grid_constant__ PipeArgs pa) {
+    extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(pipe_smem_raw);
+    __shared__ CgShared sh;
+    const CgArgs& a = pa.cg;
+    pipe_smem_init(sm);
+    cg_collective_pipe<NDIM>(a.g, a.B, a.s, pa.maps, a.rtol, a.maxiter, a.partials, a.bar, sh, sm);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.iters_out != nullptr)
+        for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
+}
+
 // u^k for small integer k the way numpy evaluates `u**nu` for nu = 2 (a multiplication); general k by repeated
 // multiplication.
 __device__ __forceinline__ double ipow(double u, int k) {
@@ -308,6 +440,80 @@ WorkLayout work_layout(int ndim, int n, int nfields) {
     return w;
 }
 
+template <int NDIM>
+int pipe_grid(int* out) {
+    static int cached = 0;
+    if (cached == 0) {
+        SDC_CUDA_OK(cudaFuncSetAttribute(cg_pipe_kernel<NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(PipeSmem)));
+        int per_sm = 0;
+        SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_pipe_kernel<NDIM>, kPipeThreads,
+                                                                  sizeof(PipeSmem)));
+        if (per_sm < 1) return fail("pipe_grid", "pipelined solver kernel does not fit on an SM");
+        if (per_sm > 2) per_sm = 2;
+        cached = per_sm * sm_count();
+    }
+    *out = cached;
+    return 0;
+}
+
+// ---- tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda) ------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int tensor_map_encoder(TensorMapEncodeFn* out) {
+    static TensorMapEncodeFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SDC_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (p == nullptr || q != cudaDriverEntryPointSuccess)
+            return fail("tensor_map_encoder", "the CUDA driver does not provide cuTensorMapEncodeTiled");
+        fn = reinterpret_cast<TensorMapEncodeFn>(p);
+    }
+    *out = fn;
+    return 0;
+}
+
+// Tiled fp64 map over a walled field: 2-D  {P, P} from element (0,0);  3-D  {P, P, nz+2} starting ONE PLANE BELOW the
+// field (guard = lower halo plane) up to and including plane nz (wall / upper halo plane).
+int encode_field_map(CUtensorMap* map, const Geom& g, const double* field, int box_x, int box_y) {
+    TensorMapEncodeFn enc = nullptr;
+    if (int rc = tensor_map_encoder(&enc)) return rc;
+    const cuuint32_t rank = (cuuint32_t)g.ndim;
+    cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.P, (cuuint64_t)(g.nz + 2)};
+    cuuint64_t strides[2] = {(cuuint64_t)g.sy * 8u, (cuuint64_t)g.sz * 8u};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    void* base = const_cast<double*>(g.ndim == 3 ? field - g.sz : field);
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("encode_field_map", "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 0;
+}
+
+template <int NDIM>
+int launch_cg_pipe(CgArgs& cg, cudaStream_t s) {
+    int grid = 0;
+    if (int rc = pipe_grid<NDIM>(&grid)) return rc;
+    if (grid > kMaxGrid) grid = kMaxGrid;
+    static thread_local PipeArgs a;  // 6 KB: kept off the stack
+    a.cg = cg;
+    for (int b = 0; b < cg.B; ++b) {
+        const Sys& S = cg.s[b];
+        if (int rc = encode_field_map(&a.maps.m[b][kMapRHalo], cg.g, S.r, kPHX, kPHY)) return rc;
+        if (int rc = encode_field_map(&a.maps.m[b][kMapPHalo], cg.g, S.p, kPHX, kPHY)) return rc;
+        if (int rc = encode_field_map(&a.maps.m[b][kMapQHalo], cg.g, S.q, kPHX, kPHY)) return rc;
+        if (int rc = encode_field_map(&a.maps.m[b][kMapRCentre], cg.g, S.r, kPX, kPY)) return rc;
+        if (int rc = encode_field_map(&a.maps.m[b][kMapXCentre], cg.g, S.x, kPX, kPY)) return rc;
+    }
+    void* params[] = {&a};
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_pipe_kernel<NDIM>, dim3(grid), dim3(kPipeThreads), params,
+                                            sizeof(PipeSmem), s));
+    return 0;
+}
+
 template <int NDIM, bool PER>
 int launch_cg(CgArgs& a, cudaStream_t s) {
     int grid = 0;
@@ -332,7 +538,7 @@ int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas)
     if (cc_major) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc_minor) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
     if (solver_ctas) {
-        if (int rc = coresident_ctas(cg_kernel<3, false>, solver_ctas)) return rc;
+        if (int rc = pipe_grid<3>(solver_ctas)) return rc;
     }
     return 0;
 }
@@ -379,8 +585,10 @@ int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_h
     int rc = 1;
     const bool per = a.g.periodic;
     if (ndim == 1) rc = per ? launch_cg<1, true>(a, s) : launch_cg<1, false>(a, s);
-    if (ndim == 2) rc = per ? launch_cg<2, true>(a, s) : launch_cg<2, false>(a, s);
-    if (ndim == 3) rc = per ? launch_cg<3, true>(a, s) : launch_cg<3, false>(a, s);
+    // heat solves on Dirichlet grids (the 2-D / 3-D benchmark configurations): bulk-async pipelined passes;
+    // periodic and 1-D grids: register-marching passes
+    if (ndim == 2) rc = per ? launch_cg<2, true>(a, s) : launch_cg_pipe<2>(a, s);
+    if (ndim == 3) rc = per ? launch_cg<3, true>(a, s) : launch_cg_pipe<3>(a, s);
     return rc;
 }
 

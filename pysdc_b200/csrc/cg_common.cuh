@@ -68,13 +68,13 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar) {
 __device__ __forceinline__ double grid_sum(const double* partials, int slot, int b, double* scratch) {
     const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
     double v = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v += __ldcg(src + i);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v += __ldcg(src + i);
     return block_sum(v, scratch);
 }
 __device__ __forceinline__ double grid_max(const double* partials, int slot, int b, double* scratch) {
     const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;
     double v = 0.0;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += kThreads) v = fmax(v, __ldcg(src + i));
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) v = fmax(v, __ldcg(src + i));
     return block_max(v, scratch);
 }
 __device__ __forceinline__ void put_partial(double* partials, int slot, int b, double v) {

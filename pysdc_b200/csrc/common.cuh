@@ -73,7 +73,7 @@ inline Geom make_slab_geom(int n, int nz, int bc) {
 // ---------------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kThreads = 256;  // every kernel in this library runs 256-thread CTAs
+constexpr int kThreads = 256;  // CTA size of the streaming / stencil kernels (block reductions read blockDim.x)
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
@@ -98,7 +98,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        double t = lane < (kThreads / 32) ? scratch[lane] : 0.0;
+        double t = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.0;
         t = warp_sum(t);
         if (lane == 0) scratch[32] = t;
     }
@@ -112,7 +112,7 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
     if (lane == 0) scratch[warp] = v;
     __syncthreads();
     if (warp == 0) {
-        double t = lane < (kThreads / 32) ? scratch[lane] : 0.0;
+        double t = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0.0;
         t = warp_max(t);
         if (lane == 0) scratch[32] = t;
     }
