@@ -97,6 +97,32 @@ int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_h
                           const double* const* rhs, double* const* x, double rtol, int maxiter,
                           void* work, size_t work_bytes, int* iters_dev, void* stream);
 
+/* ---- multi-GPU: slab decomposition of 3-D grids along the slowest axis ----------------------------------------------
+ * No reference counterpart: the reference's FD problems are not space-parallel.  One process per GPU; a
+ * rank owns nz consecutive planes of the n x n cross-section.  Slab fields use the walled layout with the guard plane
+ * as LOWER halo plane and plane nz as UPPER halo plane (volume P*P*(nz+1) doubles after the guard).
+ *
+ * Peer memory: each rank allocates its solver workspace with sdcb200_peer_alloc (zero-filled device memory + a 64-byte
+ * cudaIpc handle), ships the handle to the other ranks of the node through any host channel and maps theirs with
+ * sdcb200_peer_open.  The persistent CG kernel then exchanges the halo planes of its residual and all-reduces its dot
+ * products through that memory (NVLink loads/stores, sequence-numbered flags), with no host involvement per iteration.
+ * The caller must have put the neighbours' boundary planes into the halo planes of x (initial guess) before the call;
+ * on return the halo planes of x are stale.  All ranks must call with the same B, rtol, maxiter.                      */
+#define SDCB200_IPC_HANDLE_BYTES 64
+int sdcb200_peer_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int sdcb200_peer_open(const unsigned char* handle64, void** peer_ptr);
+int sdcb200_peer_close(void* peer_ptr);
+int sdcb200_peer_free(void* dev_ptr);
+size_t sdcb200_slab_cg_workspace_bytes(int n, int nz_max, int B);
+int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const double* m_diag_host,
+                               const double* m_off_host, const double* const* rhs, double* const* x, double rtol,
+                               int maxiter, int rank, int nranks, const int* nz_of_rank, void* const* work_of_rank,
+                               size_t work_bytes, int* iters_dev, void* stream);
+/* eval_f on a slab (halo planes of u filled by the caller) */
+int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off, int B,
+                             const double* const* u, double* const* f_impl,
+                             const double* profile, const double* gt_host, double* const* f_expl, void* stream);
+
 /* Direct solve on 1-D grids: (I - factor*A) is a constant-coefficient (cyclic) tridiagonal matrix; Thomas algorithm in
  * shared memory, one CTA per system (3 <= n <= 8192).  Replaces solver_type='direct' (scipy spsolve,
  * generic_ND_FD.py:239) for ndim == 1, the reference's CPU tutorial configuration.                                  */

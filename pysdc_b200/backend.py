@@ -42,6 +42,14 @@ def _declare(lib):
         "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, _c_dp, c_sz, _c_dp, _c_dp]),
+        "sdcb200_peer_alloc": (c_int, [c_sz, PP, ctypes.c_char_p]),
+        "sdcb200_peer_open": (c_int, [ctypes.c_char_p, PP]),
+        "sdcb200_peer_close": (c_int, [_c_dp]),
+        "sdcb200_peer_free": (c_int, [_c_dp]),
+        "sdcb200_slab_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "sdcb200_heat_cg_solve_slab": (c_int, [c_int, c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, c_int,
+                                               ctypes.POINTER(c_int), PP, c_sz, _c_dp, _c_dp]),
+        "sdcb200_heat_eval_f_slab": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int]),
         "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_d, c_d, c_d, c_d, c_int, _c_dp, _c_dp, c_d, c_int, c_d,
@@ -145,10 +153,13 @@ class CudaBackend:
     # -- K2 -----------------------------------------------------------------------------------------------------------
     def heat_eval_f(self, lay, bc, a_diag, a_off, us, fs, profile=None, gts=None, fexpls=None):
         self.launches += 1
-        self._check(self.lib.sdcb200_heat_eval_f(
-            lay.ndim, lay.n, bc, a_diag, a_off, len(us), _ptr_array(us), _ptr_array(fs),
-            None if profile is None else profile.data_ptr(), None if gts is None else _dbl_array(gts),
-            None if fexpls is None else _ptr_array(fexpls), self._stream()))
+        tail = (a_diag, a_off, len(us), _ptr_array(us), _ptr_array(fs),
+                None if profile is None else profile.data_ptr(), None if gts is None else _dbl_array(gts),
+                None if fexpls is None else _ptr_array(fexpls), self._stream())
+        if lay.is_slab:  # halo planes of us filled by the caller (SlabComm.exchange_halos)
+            self._check(self.lib.sdcb200_heat_eval_f_slab(lay.n, lay.nz, bc, *tail))
+        else:
+            self._check(self.lib.sdcb200_heat_eval_f(lay.ndim, lay.n, bc, *tail))
 
     def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs):
         self.launches += 1
@@ -166,6 +177,36 @@ class CudaBackend:
             lay.ndim, lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs), _ptr_array(xs),
             float(rtol), int(maxiter), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
 
+    # -- slab-decomposed solves over peer-mapped memory -----------------------------------------------------------------
+    def slab_cg_workspace(self, lay, comm, B):
+        """This rank's solver workspace in IPC-exportable device memory plus the mapped workspaces of all other ranks of
+        ``comm`` (collective call).  Returns a ``SlabWork`` to pass to ``heat_cg_solve_slab``."""
+        planes = comm.planes(lay.n)
+        nbytes = self.lib.sdcb200_slab_cg_workspace_bytes(lay.n, max(planes), B)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        self._check(self.lib.sdcb200_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+        handles = comm.allgather(handle.raw)
+        ptrs = []
+        for r, h in enumerate(handles):
+            if r == comm.rank:
+                ptrs.append(ptr.value)
+            else:
+                q = ctypes.c_void_p()
+                self._check(self.lib.sdcb200_peer_open(h, ctypes.byref(q)))
+                ptrs.append(q.value)
+        torch.cuda.synchronize(self.device)  # the zero-fill of every segment is complete before anybody writes into it
+        comm.barrier()
+        return SlabWork(self, comm.rank, ptrs, nbytes, planes)
+
+    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+        self.launches += 1
+        planes = (ctypes.c_int * len(work.planes))(*work.planes)
+        peers = (ctypes.c_void_p * len(work.ptrs))(*work.ptrs)
+        self._check(self.lib.sdcb200_heat_cg_solve_slab(
+            lay.n, lay.nz, max(work.planes), bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs),
+            _ptr_array(xs), float(rtol), int(maxiter), comm.rank, comm.size, planes, peers, work.nbytes,
+            iters_dev.data_ptr(), self._stream()))
+
     def heat_direct_solve_1d(self, lay, bc, m_diag, m_off, rhs, xs):
         self.launches += 1
         self._check(self.lib.sdcb200_heat_direct_solve_1d(lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off),
@@ -182,6 +223,23 @@ class CudaBackend:
             lay.n, float(factor), a_diag, a_off, inv_eps2, int(nu_exp), rhs.data_ptr(), u.data_ptr(),
             float(newton_tol), int(newton_maxiter), float(lin_tol), int(lin_maxiter),
             float(inexact_ratio or 0.0), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(), self._stream()))
+
+
+class SlabWork:
+    """Peer-mapped solver workspaces of all ranks (index = rank; own segment at ``rank``)."""
+
+    def __init__(self, backend, rank, ptrs, nbytes, planes):
+        self._be, self.rank, self.ptrs, self.nbytes, self.planes = backend, rank, ptrs, nbytes, list(planes)
+
+    def close(self):
+        if self.ptrs is None:
+            return
+        for r, p in enumerate(self.ptrs):
+            if r == self.rank:
+                self._be.lib.sdcb200_peer_free(ctypes.c_void_p(p))
+            else:
+                self._be.lib.sdcb200_peer_close(ctypes.c_void_p(p))
+        self.ptrs = None
 
 
 _backend = None

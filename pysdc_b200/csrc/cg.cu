@@ -186,21 +186,40 @@ __global__ void __launch_bounds__(kThreads) cg_kernel(const __grid_constant__ Cg
 // Dirichlet grids with a constant diagonal, i.e. the heat-equation node solves.  Launched with kPipeThreads threads
 // (8 consumer warps + 1 producer warp); the set-up pass uses the register-marching stencil on the first 8 warps.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NDIM>
+// Sum the per-CTA partials of the listed (slot, system) pairs over the grid - and, on slab runs, over all ranks -
+// leaving the results in sh.glob[i] (bit-identical on every thread of every CTA of every rank).
+template <bool SLAB>
+__device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgShared& sh, const SlabLink* link,
+                                           unsigned long long& seq, const int* slots, const int* systems, int nv) {
+    if (SLAB) grid_barrier_sys(bar);
+    else grid_barrier(bar);
+    for (int i = 0; i < nv; ++i) {
+        const double v = grid_sum(partials, slots[i], systems[i], sh.scratch);
+        if (threadIdx.x == 0) (SLAB ? sh.loc : sh.glob)[i] = v;
+    }
+    if (SLAB) cross_rank_sum(*link, sh, nv, ++seq);
+    else __syncthreads();
+}
+
+template <int NDIM, bool SLAB>
 __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const PipeMaps& maps, double rtol, int maxiter,
-                                   double* partials, unsigned* bar, CgShared& sh, PipeSmem& sm) {
+                                   double* partials, unsigned* bar, CgShared& sh, PipeSmem& sm, const SlabLink* link) {
     const Units U = make_units(g, (int)gridDim.x);
     const PUnits PU = make_punits(g, 1, (int)gridDim.x);
     const long long n2 = g.owned / 2;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gstride = (long long)gridDim.x * blockDim.x;
     unsigned kstep = 0;
+    unsigned long long seq = SLAB ? *link->seq : 0ull;
+    __shared__ int r_slots[kMailVals], r_sys[kMailVals];
 
     // ---- r = b - M x0, ||b||^2, ||r||^2 ------------------------------------------------------------------------------
     for (int b = 0; b < B; ++b) {
         const Sys& S = s[b];
         double bb = 0.0, rr = 0.0;
         if (threadIdx.x < kThreads) {
+            double* r_lo = SLAB && link->has_lo ? link->lo_r_halo[b] : nullptr;
+            double* r_hi = SLAB && link->has_hi ? link->hi_r_halo[b] : nullptr;
             for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
                 stencil_unit<NDIM, false>(g, U, S.x, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
                     const double2 rhs = ld2(S.b + idx);
@@ -208,6 +227,10 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
                     r.x = v0 ? rhs.x - fma(S.m_off, nb.x, S.m_diag * c.x) : 0.0;
                     r.y = v1 ? rhs.y - fma(S.m_off, nb.y, S.m_diag * c.y) : 0.0;
                     st2(S.r + idx, r);
+                    if (SLAB) {
+                        if (r_lo != nullptr && idx < g.sz) st2(r_lo + idx, r);
+                        if (r_hi != nullptr && idx >= g.owned - g.sz) st2(r_hi + (idx - (g.owned - g.sz)), r);
+                    }
                     if (v0) bb = fma(rhs.x, rhs.x, bb);
                     if (v1) bb = fma(rhs.y, rhs.y, bb);
                     rr = fma(r.x, r.x, rr);
@@ -220,22 +243,25 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         put_partial(partials, 0, b, bb);
         put_partial(partials, 1, b, rr);
     }
-    fence_proxy_async_global();
-    grid_barrier(bar);
-    for (int b = 0; b < B; ++b) {
-        const double bb = grid_sum(partials, 0, b, sh.scratch);
-        const double rr = grid_sum(partials, 1, b, sh.scratch);
-        if (threadIdx.x == 0) {
-            sh.bb[b] = bb;
-            sh.rr[b] = rr;
-            sh.iters[b] = 0;
-            sh.rho_prev[b] = 1.0;
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < B; ++b) {
+            r_slots[2 * b] = 0;
+            r_sys[2 * b] = b;
+            r_slots[2 * b + 1] = 1;
+            r_sys[2 * b + 1] = b;
         }
     }
+    fence_proxy_async_global();
+    reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, 2 * B);
     if (threadIdx.x == 0) {
         unsigned act = 0;
-        for (int b = 0; b < B; ++b)
-            if (sh.bb[b] != 0.0) act |= 1u << b;
+        for (int b = 0; b < B; ++b) {
+            sh.bb[b] = sh.glob[2 * b];
+            sh.rr[b] = sh.glob[2 * b + 1];
+            sh.iters[b] = 0;
+            sh.rho_prev[b] = 1.0;
+            if (sh.bb[b] != 0.0) act |= 1u << b;  // scipy: ||b|| == 0 -> return b
+        }
         sh.active = act;
     }
     __syncthreads();
@@ -256,7 +282,9 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
                     act &= ~(1u << b);
                 } else {
                     sh.beta[b] = it > 0 ? sh.rr[b] / sh.rho_prev[b] : 0.0;
-                    sm.act_list[na++] = b;
+                    sm.act_list[na] = b;
+                    r_sys[na] = b;
+                    ++na;
                 }
             }
             sh.active = act;
@@ -265,49 +293,50 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         __syncthreads();
         const unsigned act = sh.active;
         if (act == 0) break;
+        const int nact = sm.nact;
         const int cur = it & 1;  // p_new goes to (cur ? S.q : S.p), p_old is the other buffer
 
+        // ---- phase A ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
         pipe_phase_a<NDIM>(g, PU, s, maps, it == 0, cur, sh, sm, partials, kstep);
+        if (threadIdx.x < nact) r_slots[threadIdx.x] = 0;
         fence_proxy_async_global();
-        grid_barrier(bar);
-        for (int b = 0; b < B; ++b) {
-            if (!(act >> b & 1u)) continue;
-            const double pq = grid_sum(partials, 0, b, sh.scratch);
-            if (threadIdx.x == 0) sh.alpha[b] = sh.rr[b] / pq;
-        }
+        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
+        if ((int)threadIdx.x < nact) sh.alpha[r_sys[threadIdx.x]] = sh.rr[r_sys[threadIdx.x]] / sh.glob[threadIdx.x];
         __syncthreads();
 
+        // ---- phase B ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
-        pipe_phase_b<NDIM>(g, PU, s, maps, cur, sh, sm, partials, kstep);
+        pipe_phase_b<NDIM>(g, PU, s, maps, cur, sh, sm, partials, kstep, link);
+        if (threadIdx.x < nact) r_slots[threadIdx.x] = 1;
         fence_proxy_async_global();
-        grid_barrier(bar);
-        for (int b = 0; b < B; ++b) {
-            if (!(act >> b & 1u)) continue;
-            const double rr = grid_sum(partials, 1, b, sh.scratch);
-            if (threadIdx.x == 0) {
-                sh.rho_prev[b] = sh.rr[b];
-                sh.rr[b] = rr;
-                sh.iters[b] += 1;
-            }
+        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
+        if ((int)threadIdx.x < nact) {
+            const int b = r_sys[threadIdx.x];
+            sh.rho_prev[b] = sh.rr[b];
+            sh.rr[b] = sh.glob[threadIdx.x];
+            sh.iters[b] += 1;  // scipy calls the callback once per completed iteration
         }
         __syncthreads();
     }
+    if (SLAB && blockIdx.x == 0 && threadIdx.x == 0) *link->seq = seq;
 }
 
 struct PipeArgs {
     CgArgs cg;
     PipeMaps maps;
+    SlabLink link;  // used by the SLAB instantiation only
 };
 
-template <int NDIM>
+template <int NDIM, bool SLAB>
 __global__ void __launch_bounds__(kPipeThreads, 2) cg_pipe_kernel(const __grid_constant__ PipeArgs pa) {
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
     PipeSmem& sm = *reinterpret_cast<PipeSmem*>(pipe_smem_raw);
     __shared__ CgShared sh;
     const CgArgs& a = pa.cg;
     pipe_smem_init(sm);
-    cg_collective_pipe<NDIM>(a.g, a.B, a.s, pa.maps, a.rtol, a.maxiter, a.partials, a.bar, sh, sm);
+    cg_collective_pipe<NDIM, SLAB>(a.g, a.B, a.s, pa.maps, a.rtol, a.maxiter, a.partials, a.bar, sh, sm,
+                                   SLAB ? &pa.link : nullptr);
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.iters_out != nullptr)
         for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
 }
@@ -440,14 +469,37 @@ WorkLayout work_layout(int ndim, int n, int nfields) {
     return w;
 }
 
-template <int NDIM>
+// Slab workspace: identical offsets on every rank (sized for the thickest slab) so that peer addresses are
+// "peer base + my offset":  partials | barrier word | mailbox (counter, error flag, flags, values) | 3*B work fields
+struct SlabWorkLayout {
+    size_t field, guard_bytes;
+    size_t partials_off, bar_off, seq_off, err_off, flags_off, vals_off, fields_off, total;
+};
+SlabWorkLayout slab_work_layout(int n, int nz_max, int nfields) {
+    SlabWorkLayout w;
+    const size_t P = (size_t)(n + (n & 1)), sz = P * P;
+    const size_t guard = (sz + 15) / 16 * 16;
+    w.guard_bytes = guard * sizeof(double);
+    w.field = align_up((guard + sz * (size_t)(nz_max + 1)) * sizeof(double), 256);
+    w.partials_off = 0;
+    w.bar_off = align_up(2 * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
+    w.seq_off = w.bar_off + 256;
+    w.err_off = w.seq_off + 128;
+    w.flags_off = w.seq_off + 256;
+    w.vals_off = w.flags_off + align_up(2 * kMaxRanks * sizeof(unsigned long long), 256);
+    w.fields_off = w.vals_off + align_up(2 * kMaxRanks * kMailVals * sizeof(double), 256);
+    w.total = w.fields_off + (size_t)nfields * w.field;
+    return w;
+}
+
+template <int NDIM, bool SLAB>
 int pipe_grid(int* out) {
     static int cached = 0;
     if (cached == 0) {
-        SDC_CUDA_OK(cudaFuncSetAttribute(cg_pipe_kernel<NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SDC_CUDA_OK(cudaFuncSetAttribute(cg_pipe_kernel<NDIM, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(PipeSmem)));
         int per_sm = 0;
-        SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_pipe_kernel<NDIM>, kPipeThreads,
+        SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_pipe_kernel<NDIM, SLAB>, kPipeThreads,
                                                                   sizeof(PipeSmem)));
         if (per_sm < 1) return fail("pipe_grid", "pipelined solver kernel does not fit on an SM");
         if (per_sm > 2) per_sm = 2;
@@ -493,13 +545,14 @@ int encode_field_map(CUtensorMap* map, const Geom& g, const double* field, int b
     return 0;
 }
 
-template <int NDIM>
-int launch_cg_pipe(CgArgs& cg, cudaStream_t s) {
+template <int NDIM, bool SLAB = false>
+int launch_cg_pipe(CgArgs& cg, cudaStream_t s, const SlabLink* link = nullptr) {
     int grid = 0;
-    if (int rc = pipe_grid<NDIM>(&grid)) return rc;
+    if (int rc = pipe_grid<NDIM, SLAB>(&grid)) return rc;
     if (grid > kMaxGrid) grid = kMaxGrid;
     static thread_local PipeArgs a;  // 6 KB: kept off the stack
     a.cg = cg;
+    if (link != nullptr) a.link = *link;
     for (int b = 0; b < cg.B; ++b) {
         const Sys& S = cg.s[b];
         if (int rc = encode_field_map(&a.maps.m[b][kMapRHalo], cg.g, S.r, kPHX, kPHY)) return rc;
@@ -509,7 +562,7 @@ int launch_cg_pipe(CgArgs& cg, cudaStream_t s) {
         if (int rc = encode_field_map(&a.maps.m[b][kMapXCentre], cg.g, S.x, kPX, kPY)) return rc;
     }
     void* params[] = {&a};
-    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_pipe_kernel<NDIM>, dim3(grid), dim3(kPipeThreads), params,
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_pipe_kernel<NDIM, SLAB>, dim3(grid), dim3(kPipeThreads), params,
                                             sizeof(PipeSmem), s));
     return 0;
 }
@@ -538,7 +591,7 @@ int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas)
     if (cc_major) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc_minor) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
     if (solver_ctas) {
-        if (int rc = pipe_grid<3>(solver_ctas)) return rc;
+        if (int rc = pipe_grid<3, false>(solver_ctas)) return rc;
     }
     return 0;
 }
@@ -590,6 +643,70 @@ int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_h
     if (ndim == 2) rc = per ? launch_cg<2, true>(a, s) : launch_cg_pipe<2>(a, s);
     if (ndim == 3) rc = per ? launch_cg<3, true>(a, s) : launch_cg_pipe<3>(a, s);
     return rc;
+}
+
+size_t sdcb200_slab_cg_workspace_bytes(int n, int nz_max, int B) { return slab_work_layout(n, nz_max, 3 * B).total; }
+
+int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const double* m_diag_host,
+                               const double* m_off_host, const double* const* rhs, double* const* x, double rtol,
+                               int maxiter, int rank, int nranks, const int* nz_of_rank, void* const* work_of_rank,
+                               size_t work_bytes, int* iters_dev, void* stream) {
+    SDC_REQUIRE(bc == SDCB200_BC_DIRICHLET, "slab-decomposed solves are implemented for dirichlet-zero grids");
+    SDC_REQUIRE(n >= 3 && (n & 1), "dirichlet-zero grids need an odd number of points per dimension");
+    SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES, "B out of range");
+    SDC_REQUIRE(nranks >= 1 && nranks <= kMaxRanks && rank >= 0 && rank < nranks, "rank / nranks out of range");
+    SDC_REQUIRE(nz >= 1 && nz <= nz_max && nz_of_rank != nullptr && nz_of_rank[rank] == nz, "inconsistent slab sizes");
+    const SlabWorkLayout w = slab_work_layout(n, nz_max, 3 * B);
+    SDC_REQUIRE(work_of_rank != nullptr && work_bytes >= w.total, "workspace too small (see sdcb200_slab_cg_workspace_bytes)");
+    for (int r = 0; r < nranks; ++r)
+        SDC_REQUIRE(work_of_rank[r] != nullptr && (reinterpret_cast<size_t>(work_of_rank[r]) & 255u) == 0,
+                    "peer workspace missing or misaligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = make_slab_geom(n, nz, bc);
+    a.B = B;
+    a.rtol = rtol;
+    a.maxiter = maxiter;
+    char* base = static_cast<char*>(work_of_rank[rank]);
+    a.partials = reinterpret_cast<double*>(base + w.partials_off);
+    a.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
+    a.iters_out = iters_dev;
+    SlabLink L;
+    memset(&L, 0, sizeof(L));
+    L.rank = rank;
+    L.nranks = nranks;
+    L.has_lo = rank > 0;
+    L.has_hi = rank + 1 < nranks;
+    L.seq = reinterpret_cast<unsigned long long*>(base + w.seq_off);
+    L.error = reinterpret_cast<int*>(base + w.err_off);
+    for (int r = 0; r < nranks; ++r) {
+        char* pb = static_cast<char*>(work_of_rank[r]);
+        L.flags_of[r] = reinterpret_cast<unsigned long long*>(pb + w.flags_off);
+        L.vals_of[r] = reinterpret_cast<double*>(pb + w.vals_off);
+    }
+    const long long sz = a.g.sz;
+    for (int b = 0; b < B; ++b) {
+        SDC_REQUIRE(rhs[b] && x[b] && !(reinterpret_cast<size_t>(rhs[b]) & 15u) && !(reinterpret_cast<size_t>(x[b]) & 15u),
+                    "rhs / x missing or misaligned");
+        Sys& S = a.s[b];
+        S.b = rhs[b];
+        S.x = x[b];
+        const size_t off_r = w.fields_off + (size_t)(3 * b) * w.field + w.guard_bytes;
+        S.r = reinterpret_cast<double*>(base + off_r);
+        S.p = reinterpret_cast<double*>(base + off_r + w.field);
+        S.q = reinterpret_cast<double*>(base + off_r + 2 * w.field);
+        S.dvec = nullptr;
+        S.m_diag = m_diag_host[b];
+        S.m_off = m_off_host[b];
+        if (L.has_lo)  // the lower neighbour's upper halo plane: plane nz_lo of its r
+            L.lo_r_halo[b] = reinterpret_cast<double*>(static_cast<char*>(work_of_rank[rank - 1]) + off_r) +
+                             sz * nz_of_rank[rank - 1];
+        if (L.has_hi)  // the upper neighbour's lower halo plane: plane -1 of its r
+            L.hi_r_halo[b] = reinterpret_cast<double*>(static_cast<char*>(work_of_rank[rank + 1]) + off_r) - sz;
+    }
+    SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    return launch_cg_pipe<3, true>(a, s, &L);
 }
 
 size_t sdcb200_newton_workspace_bytes(int n) { return work_layout(2, n, 6).total; }

@@ -81,13 +81,102 @@ __device__ __forceinline__ void put_partial(double* partials, int slot, int b, d
     if (threadIdx.x == 0) partials[(size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x + blockIdx.x] = v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Slab decomposition over the GPUs of one NVLink/NVSwitch node: everything the persistent solver needs to talk to its
+// neighbours through PEER-MAPPED memory (cudaIpc), no host round trip and no NCCL call inside a solve.
+//   - halo exchange: the pass that updates r stores its two boundary planes straight into the neighbours' halo planes
+//   - all-reduce of the dot products: every rank writes its local sums into a mailbox slot on EVERY rank, raises a
+//     sequence-numbered flag (release at system scope) and sums the slots of all ranks in rank order, so all ranks hold
+//     bit-identical scalars and take identical branches.  Mailboxes are double-buffered by the parity of the sequence
+//     number; a rank cannot run more than one synchronisation ahead of any other.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 8;
+constexpr int kMailVals = 2 * SDCB200_MAX_NODES;  // doubles one rank publishes per synchronisation
+
+struct SlabLink {
+    int rank, nranks;
+    int has_lo, has_hi;                          // a neighbouring slab below / above
+    double* lo_r_halo[SDCB200_MAX_NODES];        // plane nz of the lower neighbour's r (its upper halo plane), per system
+    double* hi_r_halo[SDCB200_MAX_NODES];        // plane -1 of the upper neighbour's r
+    unsigned long long* flags_of[kMaxRanks];     // [2][kMaxRanks] flags in every rank's mailbox (peer-mapped; own included)
+    double* vals_of[kMaxRanks];                  // [2][kMaxRanks][kMailVals]
+    unsigned long long* seq;                     // own persistent synchronisation counter
+    int* error;                                  // own: set to 1 when a peer did not show up in time
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// grid barrier whose arrival also publishes this CTA's peer stores system-wide
+__device__ __forceinline__ void grid_barrier_sys(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned add = (blockIdx.x == 0) ? (0x80000000u - (gridDim.x - 1)) : 1u;
+        unsigned old;
+        asm volatile("atom.add.release.gpu.u32 %0,[%1],%2;" : "=r"(old) : "l"(bar), "r"(add) : "memory");
+        unsigned cur;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0,[%1];" : "=r"(cur) : "l"(bar) : "memory");
+        } while (((old ^ cur) & 0x80000000u) == 0);
+    }
+    __syncthreads();
+}
+
 // scalar state of the solver, one copy per CTA in shared memory, written by thread 0 only
 struct CgShared {
     double scratch[33];
+    double loc[kMailVals];   // slab runs: this rank's sums / the global sums of one synchronisation
+    double glob[kMailVals];
     double bb[SDCB200_MAX_NODES], rr[SDCB200_MAX_NODES], rho_prev[SDCB200_MAX_NODES];
     double alpha[SDCB200_MAX_NODES], beta[SDCB200_MAX_NODES];
     int iters[SDCB200_MAX_NODES];
     unsigned active;  // bit b set: system b still iterating
 };
+
+// Cross-rank sum of `nv` values per rank (sh.loc[0..nv) on entry, identical in every CTA of the rank).  On return
+// sh.glob[0..nv) holds the sums over all ranks, bit-identical on every thread of every rank.  Must be called by all
+// threads of all CTAs of all ranks with the same `seq` (monotonically increasing across calls and launches).
+__device__ __forceinline__ void cross_rank_sum(const SlabLink& L, CgShared& sh, int nv, unsigned long long seq) {
+    const unsigned par = (unsigned)(seq & 1ull);
+    const int t = threadIdx.x;
+    __syncthreads();
+    if (blockIdx.x == 0 && t < L.nranks) {
+        double* dst = L.vals_of[t] + ((size_t)par * kMaxRanks + L.rank) * kMailVals;
+        for (int i = 0; i < nv; ++i) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + i), "d"(sh.loc[i]) : "memory");
+        __threadfence_system();
+        unsigned long long* f = L.flags_of[t] + par * kMaxRanks + L.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+    }
+    if (t < L.nranks) {
+        const unsigned long long* f = L.flags_of[L.rank] + par * kMaxRanks + t;
+        unsigned long long v, t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            if (v >= seq) break;
+            if ((++spins & 0x3ffu) == 0) {
+                const unsigned long long now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 20000000000ull) {  // 20 s without the peer: give up loudly instead of hanging the GPU
+                    *L.error = 1;
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (t < nv) {
+        const double* src = L.vals_of[L.rank] + (size_t)par * kMaxRanks * kMailVals + t;
+        double acc = 0.0;
+        for (int r = 0; r < L.nranks; ++r) acc += __ldcg(src + (size_t)r * kMailVals);
+        sh.glob[t] = acc;
+    }
+    __syncthreads();
+}
 
 }  // namespace sdcb200

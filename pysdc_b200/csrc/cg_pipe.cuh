@@ -400,7 +400,8 @@ __device__ void pipe_phase_a(const Geom& g, const PUnits& U, const Sys* s, const
 // ---------------------------------------------------------------------------------------------------------------------
 template <int NDIM>
 __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const PipeMaps& maps, int cur,
-                             const CgShared& sh, PipeSmem& sm, double* partials, unsigned& kstep) {
+                             const CgShared& sh, PipeSmem& sm, double* partials, unsigned& kstep,
+                             const SlabLink* link = nullptr) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nact = sm.nact;
     const int P = g.P, n = g.n;
@@ -431,6 +432,7 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
         int cur_a = -1;
         double alpha = 0.0, m_diag = 0.0, m_off = 0.0;
         double *rp = nullptr, *xp = nullptr;
+        double *r_lo = nullptr, *r_hi = nullptr;  // slab runs: the neighbours' halo planes of r
         while (c.valid) {
             if (c.a != cur_a) {
                 if (cur_a >= 0) pipe_flush(sm, cur_a, rr);
@@ -442,6 +444,10 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
                 m_off = s[b].m_off;
                 rp = s[b].r;
                 xp = s[b].x;
+                if (link != nullptr) {
+                    r_lo = link->has_lo ? link->lo_r_halo[b] : nullptr;
+                    r_hi = link->has_hi ? link->hi_r_halo[b] : nullptr;
+                }
             }
             const unsigned stg = k % kPipeStages;
             mbar_wait(&sm.full[stg], (k / kPipeStages) & 1u);
@@ -480,6 +486,9 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
                 }
                 const long long idx = (NDIM == 3 ? (long long)(c.zp - 1) * g.sz : 0) + (long long)ya * g.sy + x;
                 const bool v0x = x < n, v1x = x + 1 < n;
+                // slab boundary planes of r go straight into the neighbour's halo plane (peer memory over NVLink)
+                double* push_lo = (NDIM == 3 && r_lo != nullptr && c.zp - 1 == 0) ? r_lo + (long long)ya * g.sy + x : nullptr;
+                double* push_hi = (NDIM == 3 && r_hi != nullptr && c.zp == g.nz) ? r_hi + (long long)ya * g.sy + x : nullptr;
                 if (inx && ya < n) {
                     double2 r = lds2(&B0.R[ra][2 * lane]), xv = lds2(&B0.X[ra][2 * lane]);
                     r.x = v0x ? __dsub_rn(r.x, __dmul_rn(alpha, fma(m_off, nba.x, m_diag * ca.x))) : 0.0;
@@ -488,6 +497,8 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
                     xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, ca.y));
                     st2(rp + idx, r);
                     st2(xp + idx, xv);
+                    if (push_lo != nullptr) st2(push_lo, r);
+                    if (push_hi != nullptr) st2(push_hi, r);
                     rr = fma(r.x, r.x, rr);
                     rr = fma(r.y, r.y, rr);
                 }
@@ -499,6 +510,8 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
                     xv.y = __dadd_rn(xv.y, __dmul_rn(alpha, cb.y));
                     st2(rp + idx + g.sy, r);
                     st2(xp + idx + g.sy, xv);
+                    if (push_lo != nullptr) st2(push_lo + g.sy, r);
+                    if (push_hi != nullptr) st2(push_hi + g.sy, r);
                     rr = fma(r.x, r.x, rr);
                     rr = fma(r.y, r.y, rr);
                 }

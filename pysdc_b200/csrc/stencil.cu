@@ -109,6 +109,33 @@ int sdcb200_heat_eval_f(int ndim, int n, int bc, double a_diag, double a_off, in
     return profile ? dispatch_eval<1>(a, s) : dispatch_eval<0>(a, s);
 }
 
+int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off, int B, const double* const* u,
+                             double* const* f_impl, const double* profile, const double* gt_host,
+                             double* const* f_expl, void* stream) {
+    SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES + 1, "B out of range");
+    SDC_REQUIRE(nz >= 1, "empty slab");
+    SDC_REQUIRE(bc == SDCB200_BC_PERIODIC ? !(n & 1) : (n & 1), "n parity does not match the boundary condition");
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = make_slab_geom(n, nz, bc);
+    a.B = B;
+    a.a_diag = a_diag;
+    a.a_off = a_off;
+    a.profile = profile;
+    for (int b = 0; b < B; ++b) {
+        SDC_REQUIRE(ok16(u[b]) && ok16(f_impl[b]), "u / f missing or misaligned");
+        a.u[b] = u[b];
+        a.f[b] = f_impl[b];
+        if (profile != nullptr) {
+            SDC_REQUIRE(ok16(profile) && f_expl && ok16(f_expl[b]) && gt_host, "forcing arguments missing or misaligned");
+            a.fexpl[b] = f_expl[b];
+            a.gt[b] = gt_host[b];
+        }
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return profile ? dispatch_eval<1>(a, s) : dispatch_eval<0>(a, s);
+}
+
 int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
                              const double* const* u, double* const* f, void* stream) {
     SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES + 1, "B out of range");

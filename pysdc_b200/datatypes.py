@@ -47,12 +47,14 @@ class mesh:
             ncomp = max(len(type(self).components), 1)
             if len(type(self).components) and len(shape) > 1 and shape[0] == ncomp and not self._shape_is_grid(shape):
                 shape = shape[1:]
-            self._lay = get_layout(shape)
+            comm = init[1]
+            # a slab communicator (parallel.SlabComm) decomposes 3-D grids along axis 0: `shape` is the GLOBAL shape
+            self._lay = comm.slab_layout(shape) if hasattr(comm, "slab_layout") else get_layout(shape)
             self._ncomp = ncomp
             be = get_backend()
-            self._buf = be.zeros(self._lay.guard + ncomp * self._lay.vol)
-            if init[1] is not None:
-                type(self).comm = init[1]  # class-level like the reference (mesh.py:46)
+            self._buf = be.zeros(self._lay.alloc(ncomp))
+            if comm is not None:
+                type(self).comm = comm  # class-level like the reference (mesh.py:46)
             if val != 0.0:
                 for c in range(ncomp):
                     self._lay.interior(self._comp_vol(c)).fill_(float(val))
@@ -74,8 +76,8 @@ class mesh:
         return self._buf[self._lay.guard:]
 
     def _comp_vol(self, c):
-        g, v = self._lay.guard, self._lay.vol
-        return self._buf[g + c * v: g + (c + 1) * v]
+        g, v, st = self._lay.guard, self._lay.vol, self._lay.stride
+        return self._buf[g + c * st: g + c * st + v]
 
     @property
     def flat(self):
@@ -119,6 +121,7 @@ class mesh:
                 return
             value = value.data
         elif isinstance(value, np.ndarray):
+            value = self._localize(value)
             value = torch.from_numpy(np.array(value, dtype=np.float64, order="C")).to(self._buf.device)
         if type(self).components:
             views = self._views()
@@ -135,6 +138,22 @@ class mesh:
 
     def __getitem__(self, key):
         return self.data[key]
+
+    def _localize(self, arr):
+        """Slab fields: an array of the GLOBAL grid shape is cut down to the planes this rank owns."""
+        lay = self._lay
+        if lay.is_slab and arr.shape[-3:] == lay.global_shape and lay.global_shape != lay.shape:
+            return arr[..., lay.z0: lay.z0 + lay.nz, :, :]
+        return arr
+
+    def gather(self):
+        """Global numpy array on every rank (slab fields: all-gather of the slabs; otherwise the same as ``get``)."""
+        local = self.get()
+        comm = self.comm
+        if not self._lay.is_slab or comm is None or comm.size == 1:
+            return local
+        parts = comm.allgather(local)
+        return np.concatenate(parts, axis=-3)
 
     def flatten(self):
         return self.data.reshape(-1)
@@ -246,7 +265,10 @@ class mesh:
 
     def __abs__(self):
         """Global max-norm as a Python float (mesh.py:65-83)."""
-        local = get_backend().maxabs(self.vol)
+        if self._lay.halo:  # slab fields: the halo planes between components are not part of the field
+            local = max(get_backend().maxabs(self._comp_vol(c)) for c in range(self._ncomp))
+        else:
+            local = get_backend().maxabs(self.vol)
         comm = self.comm
         if comm is not None and getattr(comm, "size", 1) > 1:
             from .comm import MAX
@@ -277,11 +299,11 @@ class MultiComponentMesh(mesh):
         comps = type(self).components
         if name in comps:
             c = comps.index(name)
-            lay, g, v = self._lay, self._lay.guard, self._lay.vol
+            lay, g, st = self._lay, self._lay.guard, self._lay.stride
             # the component's storage view starts one guard before its volume: for c > 0 that region is the previous
             # component's (zero) wall region, exactly what the stencil kernels expect in front of a field
             view = mesh.__new__(mesh)
-            mesh.__init__(view, None, _buf=self._buf[c * v: g + (c + 1) * v], _lay=lay, _ncomp=1)
+            mesh.__init__(view, None, _buf=self._buf[c * st: g + (c + 1) * st], _lay=lay, _ncomp=1)
             return view
         raise AttributeError(f"{type(self)!r} does not have attribute {name!r}!")
 

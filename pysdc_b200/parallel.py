@@ -1,0 +1,180 @@
+"""Communicators: the mpi4py-style surface the reference's datatypes / controllers use, on ``torch.distributed``.
+
+The reference talks to ``mpi4py`` (``datatype_classes/mesh.py:65-125``: ``comm.allreduce(..., op=MPI.MAX)``,
+``comm.Issend / Irecv / Bcast``; ``controller_classes/controller_MPI.py:218-305``) or, for CuPy fields, to
+``helpers/NCCL_communicator.py`` which only wraps the collectives.  Here one process drives one GPU and the transport
+is NCCL over NVLink (``torch.distributed``, backend ``nccl``; ``gloo`` with CPU tensors in the CPU test-suite):
+
+* ``TorchComm``  — rank / size, ``allreduce`` of Python scalars or lists, ``allgather`` / ``bcast`` of Python objects,
+  ``Issend / Irecv / Bcast`` of device fields with request objects (``Wait`` / ``Test``), ``barrier``.  This is what the
+  PFASST mode uses to hand ``uend`` from time slice to time slice.
+* ``SlabComm``   — a ``TorchComm`` that also describes a slab decomposition of 3-D grids along the slowest axis
+  (no reference counterpart): partition, neighbours, halo-plane exchange with grouped NCCL send/recv, and
+  the registry of peer-mapped solver workspaces (``backend.slab_cg_workspace``).  Passing it as ``comm=`` to the heat
+  problem classes turns their fields into slabs.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .comm import LAND, LOR, MAX, MIN, SUM  # noqa: F401
+from .layout import get_slab_layout
+
+_OPS = {MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN, SUM: dist.ReduceOp.SUM}
+
+
+class Request:
+    """mpi4py-like request around torch.distributed work handles."""
+
+    def __init__(self, works=()):
+        self._works = [w for w in works if w is not None]
+
+    def Wait(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+        return True
+
+    wait = Wait
+
+    def Test(self):
+        if all(w.is_completed() for w in self._works):
+            self._works = []
+            return True
+        return False
+
+    def Cancel(self):
+        self._works = []
+
+
+class TorchComm:
+    def __init__(self, group=None, device=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun / init_process_group)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        self.device = torch.device(device)
+
+    # mpi4py spellings
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.size
+
+    def _global(self, r):
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def barrier(self):
+        dist.barrier(group=self.group)
+
+    Barrier = barrier
+
+    # ---- small host values --------------------------------------------------------------------------------------------
+    def allreduce(self, value, op=SUM):
+        """Python float / int / bool or a list of them -> the same, reduced over the communicator."""
+        is_list = isinstance(value, (list, tuple, np.ndarray))
+        vals = list(value) if is_list else [value]
+        if op in (LAND, LOR):
+            t = torch.tensor([1.0 if v else 0.0 for v in vals], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN if op == LAND else dist.ReduceOp.MAX, group=self.group)
+            out = [bool(v) for v in t.tolist()]
+        else:
+            t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=_OPS[op], group=self.group)
+            out = t.tolist()
+        return out if is_list else out[0]
+
+    def allgather(self, obj):
+        out = [None] * self.size
+        dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def bcast(self, obj, root=0):
+        box = [obj]
+        dist.broadcast_object_list(box, src=self._global(root), group=self.group)
+        return box[0]
+
+    # ---- device fields (mesh.isend / irecv / bcast, mesh.py:85-125) ------------------------------------------------
+    @staticmethod
+    def _storage(field):
+        return field._buf if hasattr(field, "_buf") else field
+
+    def Issend(self, field, dest=None, tag=None):
+        return Request([dist.isend(self._storage(field), self._global(dest), group=self.group)])
+
+    Isend = Issend
+
+    def Irecv(self, field, source=None, tag=None):
+        return Request([dist.irecv(self._storage(field), self._global(source), group=self.group)])
+
+    def Send(self, field, dest=None, tag=None):
+        dist.send(self._storage(field), self._global(dest), group=self.group)
+
+    def Recv(self, field, source=None, tag=None):
+        dist.recv(self._storage(field), self._global(source), group=self.group)
+
+    def Bcast(self, field, root=0):
+        dist.broadcast(self._storage(field), src=self._global(root), group=self.group)
+
+
+def split_planes(n, size):
+    """Planes per rank: as even as possible, thicker slabs first (511 over 8 -> 7 x 64 + 63)."""
+    base, extra = divmod(int(n), int(size))
+    return [base + (1 if r < extra else 0) for r in range(size)]
+
+
+class SlabComm(TorchComm):
+    """Slab decomposition of 3-D grids along axis 0 over the ranks of the communicator."""
+
+    def __init__(self, group=None, device=None):
+        super().__init__(group, device)
+        self._work = {}
+
+    def planes(self, n):
+        counts = split_planes(n, self.size)
+        if min(counts) < 1:
+            raise ValueError(f"cannot decompose {n} planes over {self.size} ranks")
+        return counts
+
+    def slab_layout(self, shape):
+        shape = (shape,) * 3 if isinstance(shape, int) else tuple(int(s) for s in shape)
+        if len(shape) != 3 or len(set(shape)) != 1:
+            raise ValueError(f"slab decomposition needs a cubic 3-D grid, got {shape}")
+        counts = self.planes(shape[0])
+        return get_slab_layout(shape[0], counts[self.rank], sum(counts[: self.rank]))
+
+    def exchange_planes(self, quads, periodic=False):
+        """``quads`` = [(top_owned, lower_halo, bottom_owned, upper_halo), ...] contiguous plane tensors: send the top
+        owned plane up and the bottom owned plane down, receive the neighbours' planes into the halo planes."""
+        if self.size == 1:
+            if periodic:
+                for top, lower, bottom, upper in quads:
+                    lower.copy_(top)
+                    upper.copy_(bottom)
+            return
+        lo = self.rank - 1 if self.rank > 0 else (self.size - 1 if periodic else None)
+        hi = self.rank + 1 if self.rank + 1 < self.size else (0 if periodic else None)
+        ops = []
+        for top, lower, bottom, upper in quads:
+            # order matters when lo == hi (two ranks, periodic): sends / receives to one peer are matched in order
+            if hi is not None:
+                ops.append(dist.P2POp(dist.isend, top, self._global(hi), group=self.group))
+            if lo is not None:
+                ops.append(dist.P2POp(dist.irecv, lower, self._global(lo), group=self.group))
+                ops.append(dist.P2POp(dist.isend, bottom, self._global(lo), group=self.group))
+            if hi is not None:
+                ops.append(dist.P2POp(dist.irecv, upper, self._global(hi), group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def exchange_halos(self, fields, periodic=False):
+        """Fill the halo planes of single-component slab fields with the neighbours' boundary planes (grouped NCCL
+        send/recv).  At the ends of a non-periodic domain the halo planes keep their zeros (= the Dirichlet value)."""
+        self.exchange_planes([(f._lay.plane(f._buf, f._lay.nz - 1), f._lay.plane(f._buf, -1), f._lay.plane(f._buf, 0),
+                               f._lay.plane(f._buf, f._lay.nz)) for f in fields], periodic)

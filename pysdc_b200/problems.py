@@ -68,7 +68,9 @@ class HeatMixin:
     forced = False
 
     def __init__(self, nvars=512, nu=0.1, freq=2, stencil_type="center", order=2, lintol=1e-12, liniter=10000,
-                 solver_type="direct", bc="periodic", sigma=6e-2):
+                 solver_type="direct", bc="periodic", sigma=6e-2, comm=None):
+        # `comm` is the one keyword the reference does not have (its FD problems are not space-parallel): a
+        # parallel.SlabComm decomposes the 3-D grid into slabs along axis 0, one per GPU; nvars stays the GLOBAL shape
         # parameter checks of generic_ND_FD.py:99-133
         if type(nvars) not in [int, tuple]:
             raise ProblemError("nvars should be either tuple or int")
@@ -107,7 +109,11 @@ class HeatMixin:
         if solver_type == "direct" and ndim > 1:
             raise ProblemError("solver_type='direct' is implemented on the device for 1-D grids only; use 'CG'")
 
-        super().__init__(init=(nvars[0] if ndim == 1 else nvars, None, np.dtype("float64")))
+        slab = comm is not None and hasattr(comm, "slab_layout")
+        if slab and (ndim != 3 or solver_type != "CG" or bc != "dirichlet-zero"):
+            raise ProblemError("slab-decomposed runs are implemented for 3-D dirichlet-zero grids with solver_type='CG'")
+
+        super().__init__(init=(nvars[0] if ndim == 1 else nvars, comm, np.dtype("float64")))
 
         dx, xvalues = grid_1d(nvars[0], bc)
         self.xvalues = xvalues
@@ -122,7 +128,8 @@ class HeatMixin:
         self.a_diag = ((-2.0 * ndim) / dx**2) * nu
         self._bc = BC_CODES[bc]
         self._be = get_backend()
-        self._lay = get_layout(nvars)
+        self._comm = comm if slab else None
+        self._lay = comm.slab_layout(nvars) if slab else get_layout(nvars)
         self._counters = self._be.zeros(2 + 8, dtype=torch.int32)  # [total CG its, unused, per-system its of a solve]
         self._work = {}
         self._profile = None
@@ -172,6 +179,8 @@ class HeatMixin:
 
     def eval_f_batch(self, us, ts, fs):
         """fs[i] = f(us[i], ts[i]) in place, one launch for all fields."""
+        if self._comm is not None:
+            self._comm.exchange_halos(us)
         if self.forced:
             self._be.heat_eval_f(self._lay, self._bc, self.a_diag, self.a_off, [u.flat for u in us],
                                  [f.impl.flat for f in fs], self._spatial_profile().flat,
@@ -189,7 +198,10 @@ class HeatMixin:
     # -- implicit solves ----------------------------------------------------------------------------------------------
     def _cg_work(self, B):
         if B not in self._work:
-            self._work[B] = self._be.cg_workspace(self._lay, B)
+            if self._comm is not None:
+                self._work[B] = self._be.slab_cg_workspace(self._lay, self._comm, B)
+            else:
+                self._work[B] = self._be.cg_workspace(self._lay, B)
         return self._work[B]
 
     def solve_system_batch(self, rhs, factors, xs, ts=None):
@@ -207,8 +219,15 @@ class HeatMixin:
         if log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        self._be.heat_cg_solve(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs], [x.flat for x in xs],
-                               self.lintol, self.liniter, self._cg_work(len(xs)), counters)
+        if self._comm is not None:
+            # the initial guesses need their neighbours' boundary planes; the solver exchanges everything else itself
+            work = self._cg_work(len(xs))
+            self._comm.exchange_halos(xs)
+            self._be.heat_cg_solve_slab(self._lay, self._comm, self._bc, m_diag, m_off, [r.flat for r in rhs],
+                                        [x.flat for x in xs], self.lintol, self.liniter, work, counters)
+        else:
+            self._be.heat_cg_solve(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs], [x.flat for x in xs],
+                                   self.lintol, self.liniter, self._cg_work(len(xs)), counters)
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, counters.clone()))

@@ -99,9 +99,78 @@ class NumpyBackend:
             resnorm[m] = float(np.max(np.abs(acc)))
 
     # ---- K2 ---------------------------------------------------------------------------------------------------------
+    # ---- slabs: numpy views that include the two halo planes ----------------------------------------------------------
+    @staticmethod
+    def _slab_full(lay, t):
+        """(nz+2, n, n) view of a slab field: plane 0 = lower halo, 1..nz owned, nz+1 = upper halo."""
+        sz = lay.P * lay.P
+        full = t.as_strided((sz * (lay.nz + 2),), (1,), t.storage_offset() - sz)
+        return full.view(lay.nz + 2, lay.P, lay.P)[:, : lay.n, : lay.n]
+
+    def _slab_lap_sum(self, xfull, periodic):
+        """Neighbour sum on the owned planes of a slab: in-plane like _lap_sum, across planes from the halos."""
+        x = xfull[1:-1]
+        out = xfull[:-2] + xfull[2:]
+        for ax in (1, 2):
+            if periodic:
+                out = out + np.roll(x, 1, axis=ax) + np.roll(x, -1, axis=ax)
+            else:
+                add = np.zeros_like(x)
+                lo = [slice(None)] * 3
+                hi = [slice(None)] * 3
+                lo[ax], hi[ax] = slice(1, None), slice(None, -1)
+                add[tuple(lo)] += x[tuple(hi)]
+                add[tuple(hi)] += x[tuple(lo)]
+                out = out + add
+        return out
+
+    def slab_cg_workspace(self, lay, comm, B):
+        return None
+
+    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+        """Distributed CG with the same structure as the device solver: halo exchange of the search direction, global
+        dot products through the communicator; the halo planes of xs are valid on entry."""
+        from pysdc_b200.comm import SUM
+
+        self.launches += 1
+        nz = lay.nz
+        for b, (r_t, x_t) in enumerate(zip(rhs, xs)):
+            bvec = self._grid(lay, r_t).copy()
+            x = self._grid(lay, x_t)
+            dot = lambda u, v: comm.allreduce(float(np.vdot(u, v)), op=SUM)  # noqa: E731
+            bb = dot(bvec, bvec)
+            if bb == 0.0:
+                x[...] = 0.0
+                continue
+            atol = rtol * np.sqrt(bb)
+            xfull = _np(self._slab_full(lay, x_t))
+            r = bvec - (m_diag[b] * xfull[1:-1] + m_off[b] * self._slab_lap_sum(xfull, bc == 1))
+            pfull_t = torch.zeros((nz + 2, lay.n, lay.n), dtype=torch.float64)
+            pfull = pfull_t.numpy()
+            rho_prev, its = None, 0
+            for it in range(maxiter):
+                rho = dot(r, r)
+                if np.sqrt(rho) < atol:
+                    break
+                pfull[1:-1] = r if it == 0 else r + (rho / rho_prev) * pfull[1:-1]
+                comm.exchange_planes([(pfull_t[nz], pfull_t[0], pfull_t[1], pfull_t[nz + 1])], periodic=bc == 1)
+                q = m_diag[b] * pfull[1:-1] + m_off[b] * self._slab_lap_sum(pfull, bc == 1)
+                alpha = rho / dot(pfull[1:-1], q)
+                x += alpha * pfull[1:-1]
+                r -= alpha * q
+                rho_prev = rho
+                its += 1
+            iters_dev[b] += its
+
     def heat_eval_f(self, lay, bc, a_diag, a_off, us, fs, profile=None, gts=None, fexpls=None):
         self.launches += 1
         for i, (u, f) in enumerate(zip(us, fs)):
+            if lay.is_slab:
+                xfull = _np(self._slab_full(lay, u))
+                self._grid(lay, f)[...] = a_diag * xfull[1:-1] + a_off * self._slab_lap_sum(xfull, bc == 1)
+                if profile is not None:
+                    self._grid(lay, fexpls[i])[...] = self._grid(lay, profile) * gts[i]
+                continue
             x = self._grid(lay, u)
             self._grid(lay, f)[...] = a_diag * x + a_off * self._lap_sum(x, bc == 1)
             if profile is not None:

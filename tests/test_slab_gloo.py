@@ -1,0 +1,121 @@
+"""World-size-2 (and 3) `gloo` tests of the multi-GPU HOST logic on CPU: slab partition, slab datatypes, halo-plane
+exchange, global reductions, and a full SDC step through the slab-decomposed problem / sweeper classes compared with the
+single-process run.  The kernel library is replaced by the numpy test double (tests/fake_backend.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _spec(n):
+    return dict(problem_params=dict(nvars=(n, n, n), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", solver_type="CG",
+                                    lintol=1e-12, liniter=10000),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="MIN-SR-NS", initial_guess="spread"),
+                level_params=dict(dt=1e-3, restol=1e-9), step_params=dict(maxiter=20))
+
+
+def _run_step(n, comm, u0_global):
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.problems import heatNd_unforced
+    from pysdc_b200.stats import get_sorted
+    from pysdc_b200.sweepers import generic_implicit
+
+    sp = _spec(n)
+    pp = dict(sp["problem_params"])
+    if comm is not None:
+        pp["comm"] = comm
+    c = controller_nonMPI(1, {"logger_level": 40}, dict(
+        problem_class=heatNd_unforced, problem_params=pp, sweeper_class=generic_implicit,
+        sweeper_params=sp["sweeper_params"], level_params=sp["level_params"], step_params=sp["step_params"]))
+    P = c.MS[0].levels[0].prob
+    u0 = P.dtype_u(P.init)
+    u0[:] = u0_global
+    uend, stats = c.run(u0=u0, t0=0.0, Tend=1e-3)
+    niter = [v for _, v in get_sorted(stats, type="niter")]
+    return uend, niter, P
+
+
+def _worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_backend import NumpyBackend
+        from pysdc_b200 import backend
+        from pysdc_b200.datatypes import mesh
+        from pysdc_b200.parallel import SlabComm, split_planes
+
+        backend.set_backend(NumpyBackend())
+        comm = SlabComm()
+        counts = split_planes(n, world)
+        lay = comm.slab_layout((n, n, n))
+        assert lay.nz == counts[rank] and lay.z0 == sum(counts[:rank])
+
+        # datatype: global assignment is cut to the slab, abs() is global, gather() reassembles
+        rng = np.random.default_rng(7)
+        g = rng.standard_normal((n, n, n))
+        m = mesh(((n, n, n), comm, np.dtype("float64")))
+        m[:] = g
+        assert m.shape == (lay.nz, n, n)
+        assert np.array_equal(m.get(), g[lay.z0: lay.z0 + lay.nz])
+        assert abs(m) == np.max(np.abs(g))
+        assert np.array_equal(m.gather(), g)
+        assert abs(m - m) == 0.0
+
+        # halo exchange: neighbours' boundary planes arrive, domain ends keep zeros
+        comm.exchange_halos([m])
+        full = NumpyBackend._slab_full(lay, m.flat).numpy()
+        lo = g[lay.z0 - 1] if rank > 0 else np.zeros((n, n))
+        hi = g[lay.z0 + lay.nz] if rank + 1 < world else np.zeros((n, n))
+        assert np.array_equal(full[0], lo) and np.array_equal(full[-1], hi)
+
+        # a full SDC step on slabs == the single-process step
+        u0 = np.random.default_rng(1234).standard_normal((n, n, n))
+        uend, niter, P = _run_step(n, comm, u0)
+        np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.gather())
+        np.save(os.path.join(out_dir, f"niter_{rank}.npy"), np.array(niter))
+        np.save(os.path.join(out_dir, f"cg_{rank}.npy"), np.array(P.work_counters["CG"].niter))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 15), (3, 13)])
+def test_slab_step_matches_serial(tmp_path, world, n):
+    port = 29600 + world * 7 + n
+    mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_backend import NumpyBackend
+    from pysdc_b200 import backend
+    from pysdc_b200.datatypes import mesh
+
+    old, old_comm = backend._backend, mesh.comm
+    backend.set_backend(NumpyBackend())
+    try:
+        mesh.comm = None
+        u0 = np.random.default_rng(1234).standard_normal((n, n, n))
+        uend, niter, P = _run_step(n, None, u0)
+        ref = uend.get()
+        for r in range(world):
+            got = np.load(os.path.join(tmp_path, f"uend_{r}.npy"))
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+            assert list(np.load(os.path.join(tmp_path, f"niter_{r}.npy"))) == niter
+            assert abs(int(np.load(os.path.join(tmp_path, f"cg_{r}.npy"))) - P.work_counters["CG"].niter) <= 2
+    finally:
+        backend.set_backend(old)
+        mesh.comm = old_comm
+
+
+def test_split_planes():
+    from pysdc_b200.parallel import split_planes
+
+    assert split_planes(511, 8) == [64] * 7 + [63]
+    assert split_planes(511, 1) == [511]
+    assert sum(split_planes(127, 3)) == 127
