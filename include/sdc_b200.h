@@ -123,6 +123,15 @@ int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off,
                              const double* const* u, double* const* f_impl,
                              const double* profile, const double* gt_host, double* const* f_expl, void* stream);
 
+/* ---- K5: space transfer (FAS restriction / prolongation between nested grids) ---------------------------------------
+ * out[o, i, c] = sum_t W[i*width + t] * in[o, col[i*width + t], c]   (col < 0: unused slot), inner stride 1.
+ * One 1-D interpolation / restriction operator in ELL form applied along one axis of a field; N-D transfers are one
+ * call per axis.  Replaces the sparse Kronecker-product matvecs of mesh_to_mesh.restrict / prolong
+ * (transfer_classes/TransferMesh.py:149-218; operators as built by helpers/transfer_helper.py:139-247).             */
+int sdcb200_axis_apply(long long n_outer, int n_out, long long n_inner, int width, const double* W_dev,
+                       const int* col_dev, const double* in, long long in_stride_outer, long long in_stride_axis,
+                       double* out, long long out_stride_outer, long long out_stride_axis, void* stream);
+
 /* Direct solve on 1-D grids: (I - factor*A) is a constant-coefficient (cyclic) tridiagonal matrix; Thomas algorithm in
  * shared memory, one CTA per system (3 <= n <= 8192).  Replaces solver_type='direct' (scipy spsolve,
  * generic_ND_FD.py:239) for ndim == 1, the reference's CPU tutorial configuration.                                  */

@@ -50,6 +50,7 @@ def _declare(lib):
         "sdcb200_heat_cg_solve_slab": (c_int, [c_int, c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, c_int,
                                                ctypes.POINTER(c_int), PP, c_sz, _c_dp, _c_dp]),
         "sdcb200_heat_eval_f_slab": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
+        "sdcb200_axis_apply": (c_int, [c_ll, c_int, c_ll, c_int, _c_dp, _c_dp, _c_dp, c_ll, c_ll, _c_dp, c_ll, c_ll, _c_dp]),
         "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int]),
         "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_d, c_d, c_d, c_d, c_int, _c_dp, _c_dp, c_d, c_int, c_d,
@@ -206,6 +207,19 @@ class CudaBackend:
             lay.n, lay.nz, max(work.planes), bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs),
             _ptr_array(xs), float(rtol), int(maxiter), comm.rank, comm.size, planes, peers, work.nbytes,
             iters_dev.data_ptr(), self._stream()))
+
+    # -- K5 -----------------------------------------------------------------------------------------------------------
+    def upload_operator(self, W, col):
+        """ELL operator (weights, column indices) -> device tensors."""
+        return (torch.from_numpy(np.ascontiguousarray(W, dtype=np.float64)).to(self.device),
+                torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)).to(self.device))
+
+    def axis_apply(self, op, n_outer, n_out, n_inner, src, src_so, src_sa, dst, dst_so, dst_sa):
+        W, col = op
+        self.launches += 1
+        self._check(self.lib.sdcb200_axis_apply(n_outer, n_out, n_inner, W.shape[1], W.data_ptr(), col.data_ptr(),
+                                                src.data_ptr(), src_so, src_sa, dst.data_ptr(), dst_so, dst_sa,
+                                                self._stream()))
 
     def heat_direct_solve_1d(self, lay, bc, m_diag, m_off, rhs, xs):
         self.launches += 1

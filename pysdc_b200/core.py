@@ -237,7 +237,7 @@ class Step:
         for key in ("problem_class", "sweeper_class", "sweeper_params", "level_params"):
             if key not in description:
                 raise ParameterError(f"need {key} to instantiate step, only got {list(description)}")
-        self.params = Bag(maxiter=None)
+        self.params = Bag(maxiter=None, errtol=None)
         for k, v in description.get("step_params", {}).items():
             setattr(self.params, k, v)
         self.params._freeze()

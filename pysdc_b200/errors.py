@@ -3,7 +3,7 @@ against ``pySDC.core.errors`` (core/errors.py) catches what the B200 classes rai
 with the same names are defined."""
 try:  # pragma: no cover - depends on the environment
     from pySDC.core.errors import (  # noqa: F401
-        CollocationError, ControllerError, ParameterError, ProblemError, UnlockError,
+        CollocationError, ControllerError, ParameterError, ProblemError, TransferError, UnlockError,
     )
 except Exception:  # pySDC (or its qmat dependency) not installed
 
@@ -21,6 +21,9 @@ except Exception:  # pySDC (or its qmat dependency) not installed
 
     class ControllerError(Exception):
         """The controller reached an inconsistent state."""
+
+    class TransferError(Exception):
+        """A transfer class cannot work with the given levels / data."""
 
 
 class BackendError(RuntimeError):

@@ -24,27 +24,68 @@ _OPS = {MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN, SUM: dist.ReduceOp.SUM}
 
 
 class Request:
-    """mpi4py-like request around torch.distributed work handles."""
+    """mpi4py-like request around torch.distributed work handles (``after`` runs once on completion: used to copy a
+    host-staged receive back to the device when the transport cannot move device memory itself)."""
 
-    def __init__(self, works=()):
+    def __init__(self, works=(), after=None, keep=None):
         self._works = [w for w in works if w is not None]
+        self._after, self._keep = after, keep
+
+    def _finish(self):
+        self._works = []
+        if self._after is not None:
+            self._after()
+            self._after = None
+        self._keep = None
 
     def Wait(self):
         for w in self._works:
             w.wait()
-        self._works = []
+        self._finish()
         return True
 
     wait = Wait
 
     def Test(self):
         if all(w.is_completed() for w in self._works):
-            self._works = []
+            self._finish()
             return True
         return False
 
     def Cancel(self):
-        self._works = []
+        self._works, self._after, self._keep = [], None, None
+
+
+class LocalComm:
+    """Communicator of one process (serial runs of the time-parallel controller: SDC / MLSDC)."""
+
+    rank, size = 0, 1
+
+    def Get_rank(self):
+        return 0
+
+    def Get_size(self):
+        return 1
+
+    def first(self, count):
+        return self
+
+    def barrier(self):
+        pass
+
+    Barrier = barrier
+
+    def allreduce(self, value, op=SUM):
+        return value
+
+    def allgather(self, obj):
+        return [obj]
+
+    def bcast(self, obj, root=0):
+        return obj
+
+    def Bcast(self, field, root=0):
+        pass
 
 
 class TorchComm:
@@ -58,6 +99,19 @@ class TorchComm:
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
         self.device = torch.device(device)
+        self._host_staged = backend != "nccl"  # gloo moves host memory only: device fields are staged through the host
+        self._subgroups = {}
+
+    def first(self, count):
+        """Communicator of the first ``count`` ranks (``None`` on the others).  Collective over THIS communicator the
+        first time a given count is requested (torch.distributed.new_group must be entered by every rank)."""
+        if count == self.size:
+            return self
+        if count not in self._subgroups:
+            ranks = [self._global(r) for r in range(count)]
+            g = dist.new_group(ranks=ranks)
+            self._subgroups[count] = TorchComm(g, self.device) if self.rank < count else None
+        return self._subgroups[count]
 
     # mpi4py spellings
     def Get_rank(self):
@@ -105,21 +159,45 @@ class TorchComm:
         return field._buf if hasattr(field, "_buf") else field
 
     def Issend(self, field, dest=None, tag=None):
-        return Request([dist.isend(self._storage(field), self._global(dest), group=self.group)])
+        t = self._storage(field)
+        if self._host_staged and t.is_cuda:
+            h = t.cpu()
+            return Request([dist.isend(h, self._global(dest), group=self.group)], keep=h)
+        return Request([dist.isend(t, self._global(dest), group=self.group)])
 
     Isend = Issend
 
     def Irecv(self, field, source=None, tag=None):
-        return Request([dist.irecv(self._storage(field), self._global(source), group=self.group)])
+        t = self._storage(field)
+        if self._host_staged and t.is_cuda:
+            h = torch.empty(t.shape, dtype=t.dtype)
+            return Request([dist.irecv(h, self._global(source), group=self.group)], after=lambda: t.copy_(h), keep=h)
+        return Request([dist.irecv(t, self._global(source), group=self.group)])
 
     def Send(self, field, dest=None, tag=None):
-        dist.send(self._storage(field), self._global(dest), group=self.group)
+        self.Issend(field, dest, tag).Wait()
 
     def Recv(self, field, source=None, tag=None):
-        dist.recv(self._storage(field), self._global(source), group=self.group)
+        self.Irecv(field, source, tag).Wait()
 
     def Bcast(self, field, root=0):
-        dist.broadcast(self._storage(field), src=self._global(root), group=self.group)
+        t = self._storage(field)
+        if self._host_staged and t.is_cuda:
+            h = t.cpu()
+            dist.broadcast(h, src=self._global(root), group=self.group)
+            t.copy_(h)
+        else:
+            dist.broadcast(t, src=self._global(root), group=self.group)
+
+    # ---- one Python scalar between neighbours (convergence status ring, check_convergence.py:146-157) ----------
+    def send_scalar(self, value, dest):
+        t = torch.tensor([float(value)], dtype=torch.float64, device=self.device)
+        dist.send(t, self._global(dest), group=self.group)
+
+    def recv_scalar(self, source):
+        t = torch.zeros(1, dtype=torch.float64, device=self.device)
+        dist.recv(t, self._global(source), group=self.group)
+        return float(t.item())
 
 
 def split_planes(n, size):

@@ -182,6 +182,24 @@ class NumpyBackend:
             x = self._grid(lay, u)
             self._grid(lay, f)[...] = a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)
 
+    # ---- K5 ---------------------------------------------------------------------------------------------------------
+    def upload_operator(self, W, col):
+        return (torch.from_numpy(np.ascontiguousarray(W, dtype=np.float64)),
+                torch.from_numpy(np.ascontiguousarray(col, dtype=np.int32)))
+
+    def axis_apply(self, op, n_outer, n_out, n_inner, src, src_so, src_sa, dst, dst_so, dst_sa):
+        self.launches += 1
+        W, col = _np(op[0]), _np(op[1])
+        s, d = _np(src), _np(dst)
+        c = np.arange(n_inner)
+        for o in range(n_outer):
+            for i in range(n_out):
+                acc = np.zeros(n_inner)
+                for t in range(W.shape[1]):
+                    if col[i, t] >= 0:
+                        acc += W[i, t] * s[o * src_so + col[i, t] * src_sa + c]
+                d[o * dst_so + i * dst_sa + c] = acc
+
     # ---- K3 / K4 ----------------------------------------------------------------------------------------------------
     def cg_workspace(self, lay, B):
         return torch.zeros(8, dtype=torch.float64)

@@ -1,6 +1,9 @@
 """GPU parity suite (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI of libsdcb200.so; the
 expected values are the golden fixtures of the unmodified reference and, for fresh seeded inputs, the CPU oracle.
 Nothing here reads /root/reference."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -201,3 +204,73 @@ def test_midsize_3d_run_against_oracle(oracle):
     spec, _ = load_golden("run_heat3d_gi_minsrns_63_K4")
     ref = oracle.run_sdc(spec)
     assert pc.relerr(out["uend"].get(), ref["uend"]) < pc.TOL_SOLVE
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full-size checks through size-independent properties (the oracle cannot afford these sizes)
+# ---------------------------------------------------------------------------------------------------------------------
+def _solve_residual(P, factor, rhs, sol):
+    """||(I - factor*A) sol - rhs||_inf / ||rhs||_inf with A applied by the independent eval_f kernel."""
+    Au = P.eval_f(sol, 0.0)
+    Au = Au.impl if hasattr(type(Au), "components") and type(Au).components else Au
+    res = sol - factor * Au - rhs
+    return abs(res) / abs(rhs)
+
+
+@pytest.mark.parametrize("cfg", ["heat3d_511", "heat2d_2047_forced"])
+def test_fullsize_solve_properties(cfg):
+    """BASELINE.json sizes: node-batched solves satisfy their own linear systems (checked with the separate stencil
+    kernel), are linear in the right-hand side, and the operator is symmetric: <M x, y> = <x, M y>."""
+    import torch
+
+    from pysdc_b200.problems import heatNd_forced, heatNd_unforced
+
+    if cfg == "heat3d_511":
+        P = heatNd_unforced(nvars=(511, 511, 511), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", solver_type="CG",
+                            lintol=1e-12, liniter=10000)
+        factors = [1e-3 * q for q in (0.022, 0.102, 0.177, 0.25)]  # dt * diag(QDelta) of MIN-SR-NS, M = 4
+    else:
+        P = heatNd_forced(nvars=(2047, 2047), nu=0.1, freq=(4, 4), bc="dirichlet-zero", solver_type="CG", lintol=1e-12,
+                          liniter=10000)
+        factors = [0.1 * q for q in (0.05, 0.2)]
+    gen = torch.Generator(device="cuda").manual_seed(99)
+
+    def rnd():
+        m = P.dtype_u(P.init)
+        m.data.copy_(torch.randn(P.nvars, generator=gen, device="cuda", dtype=torch.float64))
+        return m
+
+    rhs = [rnd() for _ in factors]
+    xs = [P.dtype_u(P.init) for _ in factors]
+    P.solve_system_batch(rhs, factors, xs)
+    for f, b, x in zip(factors, rhs, xs):
+        assert _solve_residual(P, f, b, x) < 5e-11  # lintol 1e-12 on the 2-norm; max-norm is looser by the grid size
+    # linearity: solve(2 b0 - 3 b1) == 2 solve(b0) - 3 solve(b1) when the factor is shared
+    b01 = [rhs[0], rhs[1], 2.0 * rhs[0] - 3.0 * rhs[1]]
+    y = [P.dtype_u(P.init) for _ in b01]
+    P.solve_system_batch(b01, [factors[-1]] * 3, y)
+    assert abs(y[2] - (2.0 * y[0] - 3.0 * y[1])) / abs(y[2]) < 1e-9
+    # symmetry of the operator behind eval_f
+    u, v = rnd(), rnd()
+    Au, Av = P.eval_f(u, 0.0), P.eval_f(v, 0.0)
+    if P.forced:
+        Au, Av = Au.impl, Av.impl
+    d1, d2 = float(torch.sum(Au.data * v.data)), float(torch.sum(u.data * Av.data))
+    assert abs(d1 - d2) <= 1e-12 * max(abs(d1), abs(d2), float(torch.sum(Au.data.abs() * v.data.abs())))
+
+
+def test_slab_decomposed_run_on_two_gpus():
+    """The multi-GPU path (peer-memory CG, NCCL halo exchange) against the single-GPU path and the oracle; needs two
+    GPUs on the box (tests/mgpu/slab_check.py under torchrun)."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu", "slab_check.py"), "63"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "slab_check n=63 world=2: OK" in res.stdout
