@@ -37,6 +37,20 @@ def spec_for(n, K=K_SWEEPS):
                 t0=0.0, Tend=1e-3, u0="random", seed=1234)
 
 
+def measured_traffic(n, world):
+    """Mean DRAM bytes per CG launch from the committed ncu capture of this very command (profiles/): only meaningful
+    for the configuration it was taken on (511^3, one GPU)."""
+    try:
+        if n != 511 or world != 1:
+            return None, None
+        with open(os.path.join(ROOT, "profiles", "r01b_cg_traffic_511.json")) as f:
+            t = json.load(f)
+        per = [l["traffic"] for l in t["launches"]]
+        return float(np.mean(per)), "profiles/r01b_cg_traffic_511.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of 8 launches)"
+    except Exception:
+        return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -239,6 +253,7 @@ def run_b200(args):
         n_launch = len(solve_log)
         achieved = alg_bytes / (cg_ms * 1e-3) / 1e9
         n_cg = float(cg_iters.mean())
+        traffic, traffic_src = measured_traffic(n, world)
         value = dof_updates_per_step * args.steps / (ms * 1e-3)
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if world > 1 else "weak",
@@ -253,7 +268,9 @@ def run_b200(args):
                     gpu_launches=launches,
                     roofline=dict(bound="hbm", kernel="cg_pipe_kernel<3> (persistent node-batched CG, TMA-pipelined passes)"
                                   + (", rank 0's slab" if world > 1 else ""), achieved=achieved,
-                                  peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src, traffic=None,
+                                  peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src, traffic=traffic,
+                                  traffic_unit="bytes per launch", traffic_source=traffic_src,
+                                  algorithmic_bytes_per_launch=alg_bytes / max(n_launch, 1),
                                   launches=n_launch, ms_per_launch=cg_ms / max(n_launch, 1),
                                   share_of_step=cg_ms / ms,
                                   whole_step_achieved=(84 + 72 * n_cg) * dof_updates_per_step * args.steps / (ms * 1e-3) / 1e9),

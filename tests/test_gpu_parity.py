@@ -274,3 +274,21 @@ def test_slab_decomposed_run_on_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "slab_check n=63 world=2: OK" in res.stdout
+
+
+@pytest.mark.parametrize("name,world", [("pfasst_heat2d_imex_63_p4", 4), ("pfasst_step8A_heat1d", 8)])
+def test_pfasst_time_slices(name, world):
+    """PFASST with one process per time slice on the real kernels vs the reference's fixtures.  With enough GPUs the
+    slices run one per GPU over NCCL; on a single-GPU box they share the device and hand over through gloo."""
+    import subprocess
+
+    import torch
+
+    transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(29540 + world), os.path.join(root, "tests", "mgpu", "pfasst_check.py"),
+           name, transport]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert ": OK" in res.stdout
