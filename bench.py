@@ -238,6 +238,43 @@ def run_b200(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
+    # ---- the streaming kernels of the sweep on their own (north_star: "collocation integration ... one coalesced
+    # kernel fused with the rhs assembly and the residual norm"): algorithmic bytes / CUDA-event time ----------------
+    other = {}
+    if rank == 0 and world == 1:
+        L = ctrl.MS[0].levels[0]
+        sweep = L.sweep
+        nloc = nz * n * n
+        reps = 10
+
+        def timed(fn):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        fins = sweep._f_inputs(L)
+        rhs = sweep._scratch(L, M_NODES)
+        W = np.random.default_rng(0).standard_normal((M_NODES, len(fins)))
+        norms = be.zeros(M_NODES)
+        kernels = {
+            "colloc_apply_kernel<4> (rhs assembly: u0 + dt(Q-QD)F)":
+                (lambda: be.colloc_apply(W, fins, L.u[0].flat, None, [r.flat for r in rhs]), 8 * (2 * M_NODES + 1)),
+            "colloc_residual_kernel<4> (residual + max-norms)":
+                (lambda: be.colloc_residual(W, fins, L.u[0].flat, [u.flat for u in L.u[1:]], None, None, norms),
+                 8 * (2 * M_NODES + 1)),
+            "eval_f_kernel<3> (4 fields)":
+                (lambda: P.eval_f_batch(L.u[1:], [0.0] * M_NODES, L.f[1:]), 16 * M_NODES),
+        }
+        for name, (fn, bytes_per_dof) in kernels.items():
+            t_ms = timed(fn)
+            gbs = bytes_per_dof * nloc / (t_ms * 1e-3) / 1e9
+            other[name] = dict(ms=t_ms, algorithmic_bytes=bytes_per_dof * nloc, achieved_gbs=gbs)
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -274,6 +311,7 @@ def run_b200(args):
                                   launches=n_launch, ms_per_launch=cg_ms / max(n_launch, 1),
                                   share_of_step=cg_ms / ms,
                                   whole_step_achieved=(84 + 72 * n_cg) * dof_updates_per_step * args.steps / (ms * 1e-3) / 1e9),
+                    other_kernels={k: dict(v, frac_of_peak=v["achieved_gbs"] / peak) for k, v in other.items()},
                     clocks=clocks)
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_rate(args.ref_n, K_SWEEPS)

@@ -400,7 +400,7 @@ def pfasst_config5():
     # of this run sit close to restol, the histories document how close
     hist = {}
     for k, v in stats.items():
-        if k.type == "residual_post_iteration" and k.level == 0:
+        if k.type == "residual_post_iteration":
             hist.setdefault(round(k.time, 10), {})[k.iter] = float(v)
     res = np.full((len(hist), max(niter)), np.nan)
     for i, t in enumerate(sorted(hist)):

@@ -209,62 +209,73 @@ class BaseTransfer:
         """Lagrange interpolation matrix from ``c_nodes`` to ``f_nodes`` (base_transfer.py:79-91)."""
         return np.array([_lagrange_weights(c_nodes, p) for p in f_nodes])
 
+    # ---- node-to-node combinations as fused launches -----------------------------------------------------------------
+    @staticmethod
+    def _parts(x):
+        comps = type(x).components
+        return [getattr(x, c) for c in comps] if comps else [x]
+
+    def _combine(self, weights, fields, like_init, dtype, base=None, subtract=None):
+        """out[n] = (base[n] if given) + sum_m weights[n, m] * fields[m] (- subtract[n] if given) for all n at once:
+        one fused collocation launch per component instead of the reference's nested axpy loops."""
+        be = get_backend()
+        weights = np.atleast_2d(np.asarray(weights, dtype=float))
+        outs = [dtype(like_init) for _ in range(weights.shape[0])]
+        W = weights if subtract is None else np.hstack([weights, -np.eye(weights.shape[0])])
+        for c in range(len(self._parts(outs[0]))):
+            ins = [self._parts(f)[c].flat for f in fields]
+            if subtract is not None:
+                ins += [self._parts(t)[c].flat for t in subtract]
+            adds = None if base is None else [self._parts(b)[c].flat for b in base]
+            be.colloc_apply(W, ins, None, adds, [self._parts(o)[c].flat for o in outs])
+        return outs
+
     def restrict(self):
-        """base_transfer.py:93-168."""
+        """Space-time restriction with FAS correction (base_transfer.py:93-168): coarse values = Rcoll x (space-
+        restricted fine values), coarse right-hand sides re-evaluated, tau = R(Q_f F_f) - Q_c F_c (+ restricted fine
+        tau)."""
         F, G = self.fine, self.coarse
         PG, SF, SG = G.prob, F.sweep, G.sweep
         if not F.status.unlocked:
             raise UnlockError("fine level is still locked, cannot use data from there")
         MF, MG = SF.coll.num_nodes, SG.coll.num_nodes
-        tmp_u = [self.space_transfer.restrict(F.u[m]) for m in range(1, MF + 1)]
-        G.u[0] = self.space_transfer.restrict(F.u[0])
-        for n in range(1, MG + 1):
-            G.u[n] = self.Rcoll[n - 1, 0] * tmp_u[0]
-            for m in range(1, MF):
-                G.u[n] += self.Rcoll[n - 1, m] * tmp_u[m]
-        G.f[0] = PG.eval_f(G.u[0], G.time)
-        for m in range(1, MG + 1):
-            G.f[m] = PG.eval_f(G.u[m], G.time + G.dt * SG.coll.nodes[m - 1])
-        tauG = G.sweep.integrate()
-        tauF = F.sweep.integrate()
-        tmp_tau = [self.space_transfer.restrict(tauF[m]) for m in range(MF)]
-        for n in range(1, MG + 1):
-            t = self.Rcoll[n - 1, 0] * tmp_tau[0]
-            for m in range(1, MF):
-                t += self.Rcoll[n - 1, m] * tmp_tau[m]
-            G.tau[n - 1] = t - tauG[n - 1]
+        R = self.space_transfer.restrict
+        G.u[0] = R(F.u[0])
+        G.u[1:] = self._combine(self.Rcoll, [R(F.u[m]) for m in range(1, MF + 1)], PG.init, PG.dtype_u)
+        times = [G.time] + [G.time + G.dt * SG.coll.nodes[m] for m in range(MG)]
+        for m in range(MG + 1):
+            G.f[m] = PG.eval_f(G.u[m], times[m])
+        tau_coarse = G.sweep.integrate()
+        restricted = [R(t) for t in F.sweep.integrate()]
+        G.tau[:] = self._combine(self.Rcoll, restricted, PG.init, PG.dtype_u, subtract=tau_coarse)
         if F.tau[0] is not None:
-            tmp_tau = [self.space_transfer.restrict(F.tau[m]) for m in range(MF)]
-            for n in range(MG):
-                for m in range(MF):
-                    G.tau[n] += self.Rcoll[n, m] * tmp_tau[m]
+            G.tau[:] = self._combine(self.Rcoll, [R(t) for t in F.tau], PG.init, PG.dtype_u, base=G.tau)
         for m in range(1, MG + 1):
             G.uold[m] = PG.dtype_u(G.u[m])
             G.fold[m] = PG.dtype_f(G.f[m])
         G.status.unlocked = True
 
+    def _correct(self, fine_list, coarse_new, coarse_old, init, dtype):
+        """fine[n] += sum_m Pcoll[n, m] * prolong(coarse_new[m] - coarse_old[m])."""
+        MG = self.coarse.sweep.coll.num_nodes
+        delta = [self.space_transfer.prolong(coarse_new[m] - coarse_old[m]) for m in range(1, MG + 1)]
+        fine_list[1:] = self._combine(self.Pcoll, delta, init, dtype, base=fine_list[1:])
+
     def prolong(self):
-        """base_transfer.py:170-215."""
+        """Coarse correction of the fine values, fine right-hand sides re-evaluated (base_transfer.py:170-215)."""
         F, G = self.fine, self.coarse
-        PF, SF, SG = F.prob, F.sweep, G.sweep
         if not G.status.unlocked:
             raise UnlockError("coarse level is still locked, cannot use data from there")
-        tmp_u = [self.space_transfer.prolong(G.u[m] - G.uold[m]) for m in range(1, SG.coll.num_nodes + 1)]
-        for n in range(1, SF.coll.num_nodes + 1):
-            for m in range(SG.coll.num_nodes):
-                F.u[n] += self.Pcoll[n - 1, m] * tmp_u[m]
+        PF, SF = F.prob, F.sweep
+        self._correct(F.u, G.u, G.uold, PF.init, PF.dtype_u)
         for m in range(1, SF.coll.num_nodes + 1):
             F.f[m] = PF.eval_f(F.u[m], F.time + F.dt * SF.coll.nodes[m - 1])
 
     def prolong_f(self):
-        """base_transfer.py:217-251."""
+        """Coarse correction of values AND right-hand sides, no re-evaluation (base_transfer.py:217-251)."""
         F, G = self.fine, self.coarse
-        SF, SG = F.sweep, G.sweep
         if not G.status.unlocked:
             raise UnlockError("coarse level is still locked, cannot use data from there")
-        tmp_u = [self.space_transfer.prolong(G.u[m] - G.uold[m]) for m in range(1, SG.coll.num_nodes + 1)]
-        tmp_f = [self.space_transfer.prolong(G.f[m] - G.fold[m]) for m in range(1, SG.coll.num_nodes + 1)]
-        for n in range(1, SF.coll.num_nodes + 1):
-            for m in range(SG.coll.num_nodes):
-                F.u[n] += self.Pcoll[n - 1, m] * tmp_u[m]
-                F.f[n] += self.Pcoll[n - 1, m] * tmp_f[m]
+        PF = F.prob
+        self._correct(F.u, G.u, G.uold, PF.init, PF.dtype_u)
+        self._correct(F.f, G.f, G.fold, PF.init, PF.dtype_f)

@@ -23,7 +23,7 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     if transport == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
-        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        dist.init_process_group("nccl")  # lazy init: point-to-point pairs get their own 2-rank communicators
     else:
         torch.cuda.set_device(0)
         dist.init_process_group("gloo")

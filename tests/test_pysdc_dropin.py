@@ -63,3 +63,28 @@ def test_reference_controller_drives_plugin_classes(plugin, name):
         got = [int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")]
         want = g["work_" + key].tolist()
         assert np.all(np.abs(np.array(got) - np.array(want)) <= np.maximum(np.ceil(0.02 * np.array(want)), 1)), (key, got, want)
+
+
+def test_reference_pfasst_controller_drives_plugin_classes(plugin):
+    """PFASST through the reference's OWN virtual-parallel controller, base transfer and convergence controllers, with
+    the device problem / sweeper / space-transfer classes plugged in: same iteration counts and end value as the
+    reference's classes gave (fixture pfasst_heat2d_imex_63_p4)."""
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+
+    from pysdc_b200.transfer import mesh_to_mesh
+
+    spec, g = load_golden("pfasst_heat2d_imex_63_p4")
+    pp = dict(spec["problem_params"])
+    pp["nvars"] = [tuple(v) for v in pp["nvars"]]
+    pp["freq"] = tuple(pp["freq"])
+    d = dict(problem_class=getattr(plugin, spec["problem"]), problem_params=pp,
+             sweeper_class=getattr(plugin, spec["sweeper"]), sweeper_params=dict(spec["sweeper_params"]),
+             level_params=dict(spec["level_params"]), step_params=dict(spec["step_params"]),
+             space_transfer_class=mesh_to_mesh, space_transfer_params=dict(spec["space_transfer_params"]))
+    c = controller_nonMPI(num_procs=spec["num_procs"], controller_params=dict(spec["controller_params"]), description=d)
+    P = c.MS[0].levels[0].prob
+    uend, stats = c.run(u0=P.u_exact(0.0), t0=0.0, Tend=spec["Tend"])
+    niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
+    assert niter == g["niter"].tolist()
+    assert np.max(np.abs(uend.get() - g["uend"])) / np.max(np.abs(g["uend"])) < 1e-10
