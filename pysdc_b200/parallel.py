@@ -47,6 +47,8 @@ class Request:
     wait = Wait
 
     def Test(self):
+        if not self._works:
+            return True
         if all(w.is_completed() for w in self._works):
             self._finish()
             return True

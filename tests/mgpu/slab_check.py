@@ -61,6 +61,22 @@ def main():
 
     uend_slab, niter_slab = run(dict(pp, comm=comm))
     uend_slab = uend_slab.gather()
+
+    # forced heat, IMEX sweeper with LU (sequential node solves, one system per launch) on slabs
+    from pysdc_b200.problems import heatNd_forced
+    from pysdc_b200.sweepers import imex_1st_order
+
+    def run_imex(extra):
+        c = controller_nonMPI(1, {"logger_level": 40}, dict(
+            problem_class=heatNd_forced, problem_params=dict(pp, freq=(2, 2, 2), **extra), sweeper_class=imex_1st_order,
+            sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+            level_params=dict(dt=5e-3, restol=1e-9), step_params=dict(maxiter=50)))
+        Pr = c.MS[0].levels[0].prob
+        uend, stats = c.run(u0=Pr.u_exact(0.0), t0=0.0, Tend=1e-2)
+        return uend, [v for _, v in get_sorted(stats, type="niter")]
+
+    uend_imex_slab, niter_imex_slab = run_imex(dict(comm=comm))
+    uend_imex_slab = uend_imex_slab.gather()
     torch.cuda.synchronize()
     dist.barrier()
 
@@ -74,13 +90,17 @@ def main():
         P1.solve_system_batch([to_mesh(P1, rhs_g) for _ in factors], factors, x1)
         uend_one, niter_one = run(dict(pp))
         uend_one = uend_one.get()
+        uend_imex_one, niter_imex_one = run_imex({})
+        uend_imex_one = uend_imex_one.get()
         rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))  # noqa: E731
         checks = {"eval_f bitwise": bool(np.array_equal(f_slab, f_one)),
                   "solve vs 1 GPU": max(rel(a, b.get()) for a, b in zip(sol_slab, x1)),
                   "CG its slab / 1 GPU": (cg_slab, P1.work_counters["CG"].niter),
-                  "uend vs 1 GPU": rel(uend_slab, uend_one), "niter": (niter_slab, niter_one)}
+                  "uend vs 1 GPU": rel(uend_slab, uend_one), "niter": (niter_slab, niter_one),
+                  "imex uend vs 1 GPU": rel(uend_imex_slab, uend_imex_one), "imex niter": (niter_imex_slab, niter_imex_one)}
         ok = checks["eval_f bitwise"] and checks["solve vs 1 GPU"] < 1e-10 and checks["uend vs 1 GPU"] < 1e-10 \
-            and niter_slab == niter_one and abs(cg_slab - P1.work_counters["CG"].niter) <= 4
+            and niter_slab == niter_one and abs(cg_slab - P1.work_counters["CG"].niter) <= 4 \
+            and checks["imex uend vs 1 GPU"] < 1e-10 and niter_imex_slab == niter_imex_one
         if n <= 63:
             import sdc_oracle
 
