@@ -43,10 +43,10 @@ def measured_traffic(n, world):
     try:
         if n != 511 or world != 1:
             return None, None
-        with open(os.path.join(ROOT, "profiles", "r01b_cg_traffic_511.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "cg_traffic_511.json")) as f:
             t = json.load(f)
         per = [l["traffic"] for l in t["launches"]]
-        return float(np.mean(per)), "profiles/r01b_cg_traffic_511.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of 8 launches)"
+        return float(np.mean(per)), "profiles/cg_traffic_511.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of 8 launches)"
     except Exception:
         return None, None
 
