@@ -135,19 +135,24 @@ __device__ __forceinline__ void stencil_unit_ld(const Geom& g, const Units& U, c
     const bool zwrap = PER && NDIM == 3 && !g.zhalo;
 
     long long idx = row + xs + (NDIM == 3 ? (long long)z0 * g.sz : 0);
-    double2 c_prev = make_double2(0.0, 0.0), c_next = make_double2(0.0, 0.0);
+    double2 c_prev = make_double2(0.0, 0.0), c_next = make_double2(0.0, 0.0), c_next2 = make_double2(0.0, 0.0);
     double2 c = ld.pair(idx);
+    // plane z lives at offset plane_off(z) from plane z0 (periodic grids wrap; slabs and Dirichlet grids have real
+    // planes at -1 and nz: halo / guard / wall)
+    auto plane_off = [&](int z) -> long long {
+        if (zwrap) z = z < 0 ? z + g.nz : (z >= g.nz ? z - g.nz : z);
+        return (long long)(z - z0) * g.sz;
+    };
+    const long long base = idx;
     if constexpr (NDIM == 3) {
-        long long below = -g.sz;
-        if (zwrap && z0 == 0) below = (long long)(g.nz - 1) * g.sz;
-        c_prev = ld.pair(idx + below);
-        if (g.zhalo && z0 == 0 && inx) h(idx + below, c_prev);
+        c_prev = ld.pair(base + plane_off(z0 - 1));
+        if (g.zhalo && z0 == 0 && inx) h(base + plane_off(-1), c_prev);
+        c_next = ld.pair(base + plane_off(z0 + 1));
     }
     for (int z = z0; z < z1; ++z) {
         if constexpr (NDIM == 3) {
-            long long above = g.sz;
-            if (zwrap && z == g.nz - 1) above = -(long long)(g.nz - 1) * g.sz;
-            c_next = ld.pair(idx + above);
+            // the plane after next is requested one step early: two DRAM-bound loads in flight per warp instead of one
+            if (z + 1 < z1) c_next2 = ld.pair(base + plane_off(z + 2));
         }
         // x direction: shuffles inside the warp, two edge lanes load from the neighbouring tile / wrap around
         double left = __shfl_up_sync(0xffffffffu, c.y, 1);
@@ -174,6 +179,7 @@ __device__ __forceinline__ void stencil_unit_ld(const Geom& g, const Units& U, c
         if constexpr (NDIM == 3) {
             c_prev = c;
             c = c_next;
+            c_next = c_next2;
             idx += g.sz;
         }
     }
