@@ -38,6 +38,9 @@ extern "C" {
 #define SDCB200_BC_DIRICHLET 0
 #define SDCB200_BC_PERIODIC 1
 
+#define SDCB200_PRECOND_NONE 0        /* plain CG: the reference's algorithm, iteration for iteration */
+#define SDCB200_PRECOND_CHEBYSHEV1 1  /* CG preconditioned with a degree-1 Chebyshev polynomial in the operator */
+
 int sdcb200_version(void);
 const char* sdcb200_last_error(void);
 /* SM count, compute capability and co-resident CTA capacity of the persistent solver kernel on the current device */
@@ -90,11 +93,14 @@ int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2
  * all B systems inside ONE persistent cooperative launch (device-side reductions, grid barriers, per-system
  * convergence).  Replaces GenericNDimFinDiff.solve_system with solver_type='CG' (generic_ND_FD.py:252-260).
  * m_diag[b] = 1 - factor_b*a_diag, m_off[b] = -factor_b*a_off (host arrays).  iters_dev[b] += iterations used.
+ * precond = SDCB200_PRECOND_CHEBYSHEV1 (2-D / 3-D dirichlet-zero grids) preconditions the iteration with
+ * z = a r + b M r, the degree-1 Chebyshev polynomial for the known spectrum (1, 1 + 4 ndim factor a_off) of M: the same
+ * stopping test on ||r||, about half the iterations, one more stencil pass per iteration.
  * work must hold sdcb200_cg_workspace_bytes() bytes of device memory, 256-byte aligned, ZERO-FILLED by the caller
  * before its first use and otherwise left alone between calls (the solver keeps the walls of its work fields zero).  */
 size_t sdcb200_cg_workspace_bytes(int ndim, int n, int B);
 int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
-                          const double* const* rhs, double* const* x, double rtol, int maxiter,
+                          const double* const* rhs, double* const* x, double rtol, int maxiter, int precond,
                           void* work, size_t work_bytes, int* iters_dev, void* stream);
 
 /* ---- multi-GPU: slab decomposition of 3-D grids along the slowest axis ----------------------------------------------
@@ -116,8 +122,8 @@ int sdcb200_peer_free(void* dev_ptr);
 size_t sdcb200_slab_cg_workspace_bytes(int n, int nz_max, int B);
 int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const double* m_diag_host,
                                const double* m_off_host, const double* const* rhs, double* const* x, double rtol,
-                               int maxiter, int rank, int nranks, const int* nz_of_rank, void* const* work_of_rank,
-                               size_t work_bytes, int* iters_dev, void* stream);
+                               int maxiter, int precond, int rank, int nranks, const int* nz_of_rank,
+                               void* const* work_of_rank, size_t work_bytes, int* iters_dev, void* stream);
 /* eval_f on a slab (halo planes of u filled by the caller) */
 int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off, int B,
                              const double* const* u, double* const* f_impl,

@@ -41,14 +41,15 @@ def _declare(lib):
         "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
-        "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, _c_dp, c_sz, _c_dp, _c_dp]),
+        "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, _c_dp, c_sz, _c_dp,
+                                          _c_dp]),
         "sdcb200_peer_alloc": (c_int, [c_sz, PP, ctypes.c_char_p]),
         "sdcb200_peer_open": (c_int, [ctypes.c_char_p, PP]),
         "sdcb200_peer_close": (c_int, [_c_dp]),
         "sdcb200_peer_free": (c_int, [_c_dp]),
         "sdcb200_slab_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "sdcb200_heat_cg_solve_slab": (c_int, [c_int, c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, c_int,
-                                               ctypes.POINTER(c_int), PP, c_sz, _c_dp, _c_dp]),
+                                               c_int, ctypes.POINTER(c_int), PP, c_sz, _c_dp, _c_dp]),
         "sdcb200_heat_eval_f_slab": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_axis_apply": (c_int, [c_ll, c_int, c_ll, c_int, _c_dp, _c_dp, _c_dp, c_ll, c_ll, _c_dp, c_ll, c_ll, _c_dp]),
         "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
@@ -172,11 +173,12 @@ class CudaBackend:
         nbytes = self.lib.sdcb200_cg_workspace_bytes(lay.ndim, lay.n, B)
         return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
 
-    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev, precond=0):
         self.launches += 1
         self._check(self.lib.sdcb200_heat_cg_solve(
             lay.ndim, lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs), _ptr_array(xs),
-            float(rtol), int(maxiter), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
+            float(rtol), int(maxiter), int(precond), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(),
+            self._stream()))
 
     # -- slab-decomposed solves over peer-mapped memory -----------------------------------------------------------------
     def slab_cg_workspace(self, lay, comm, B):
@@ -199,13 +201,13 @@ class CudaBackend:
         comm.barrier()
         return SlabWork(self, comm.rank, ptrs, nbytes, planes)
 
-    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev, precond=0):
         self.launches += 1
         planes = (ctypes.c_int * len(work.planes))(*work.planes)
         peers = (ctypes.c_void_p * len(work.ptrs))(*work.ptrs)
         self._check(self.lib.sdcb200_heat_cg_solve_slab(
             lay.n, lay.nz, max(work.planes), bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs),
-            _ptr_array(xs), float(rtol), int(maxiter), comm.rank, comm.size, planes, peers, work.nbytes,
+            _ptr_array(xs), float(rtol), int(maxiter), int(precond), comm.rank, comm.size, planes, peers, work.nbytes,
             iters_dev.data_ptr(), self._stream()))
 
     # -- K5 -----------------------------------------------------------------------------------------------------------

@@ -13,6 +13,9 @@ struct Sys {
     const double* dvec;  // optional full diagonal of the operator (Allen-Cahn Jacobian); NULL -> m_diag
     double m_diag;       // 1 - factor*a_diag
     double m_off;        // -factor*a_off
+    // polynomial preconditioner  z = pc_a * r + pc_b * (M r)  (degree-1 Chebyshev polynomial in M); z == NULL: none
+    double* z;
+    double pc_a, pc_b;
 };
 
 struct CgArgs {
@@ -98,6 +101,8 @@ struct SlabLink {
     int has_lo, has_hi;                          // a neighbouring slab below / above
     double* lo_r_halo[SDCB200_MAX_NODES];        // plane nz of the lower neighbour's r (its upper halo plane), per system
     double* hi_r_halo[SDCB200_MAX_NODES];        // plane -1 of the upper neighbour's r
+    double* lo_z_halo[SDCB200_MAX_NODES];        // the same for the preconditioned residual z (preconditioned runs)
+    double* hi_z_halo[SDCB200_MAX_NODES];
     unsigned long long* flags_of[kMaxRanks];     // [2][kMaxRanks] flags in every rank's mailbox (peer-mapped; own included)
     double* vals_of[kMaxRanks];                  // [2][kMaxRanks][kMailVals]
     unsigned long long* seq;                     // own persistent synchronisation counter
@@ -132,6 +137,7 @@ struct CgShared {
     double loc[kMailVals];   // slab runs: this rank's sums / the global sums of one synchronisation
     double glob[kMailVals];
     double bb[SDCB200_MAX_NODES], rr[SDCB200_MAX_NODES], rho_prev[SDCB200_MAX_NODES];
+    double rz[SDCB200_MAX_NODES];  // r.z of the preconditioned solver (== rr without a preconditioner)
     double alpha[SDCB200_MAX_NODES], beta[SDCB200_MAX_NODES];
     int iters[SDCB200_MAX_NODES];
     unsigned active;  // bit b set: system b still iterating

@@ -58,7 +58,7 @@ static_assert(offsetof(StageA, P) % 128 == 0 && offsetof(StageB, R) % 128 == 0 &
               "TMA box destinations must be 128-byte aligned");
 
 // tensor maps of one system: boxes with halo of r and both direction buffers, tile-only boxes of r and x
-enum { kMapRHalo = 0, kMapPHalo, kMapQHalo, kMapRCentre, kMapXCentre, kMapsPerSys };
+enum { kMapRHalo = 0, kMapPHalo, kMapQHalo, kMapRCentre, kMapXCentre, kMapZHalo, kMapsPerSys };
 struct PipeMaps {
     CUtensorMap m[SDCB200_MAX_NODES][kMapsPerSys];
 };
@@ -275,7 +275,9 @@ __device__ void pipe_phase_a(const Geom& g, const PUnits& U, const Sys* s, const
             if (lane == 0) {
                 const CUtensorMap* mp = maps.m[sm.act_list[c.a]];
                 StageA& A = sm.st[stg].a;
-                const CUtensorMap* hsrc[2] = {mp + kMapRHalo, mp + (cur ? kMapPHalo : kMapQHalo)};  // r, p_old
+                // r (or the preconditioned residual z), p_old
+                const CUtensorMap* hsrc[2] = {mp + (s[sm.act_list[c.a]].z != nullptr ? kMapZHalo : kMapRHalo),
+                                              mp + (cur ? kMapPHalo : kMapQHalo)};
                 void* hdst[2] = {A.R, A.P};
                 pipe_issue<NDIM>(c, hsrc, first ? 1 : 2, hdst, nullptr, 0, nullptr, &sm.full[stg]);
             }
@@ -532,6 +534,134 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
     }
     kstep = k;
     pipe_publish(sm, partials, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// phase C (preconditioned runs):  z = pc_a r + pc_b M r,  r.z      stage = rows of r with the halo ring
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NDIM>
+__device__ void pipe_phase_c(const Geom& g, const PUnits& U, const Sys* s, const PipeMaps& maps, PipeSmem& sm,
+                             double* partials, unsigned& kstep, const SlabLink* link = nullptr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nact = sm.nact;
+    const int P = g.P, n = g.n;
+    pipe_begin(sm);
+    StepCursor c;
+    cursor_init<NDIM>(c, U, g, nact);
+    unsigned k = kstep;
+    if (warp == kPipeConsumers) {
+        while (c.valid) {
+            const unsigned stg = k % kPipeStages;
+            if (k >= kPipeStages) mbar_wait(&sm.empty[stg], ((k / kPipeStages) - 1u) & 1u);
+            if (lane == 0) {
+                const CUtensorMap* mp = maps.m[sm.act_list[c.a]];
+                const CUtensorMap* hsrc[1] = {mp + kMapRHalo};
+                void* hdst[1] = {sm.st[stg].a.R};
+                pipe_issue<NDIM>(c, hsrc, 1, hdst, nullptr, 0, nullptr, &sm.full[stg]);
+            }
+            ++k;
+            cursor_next<NDIM>(c, U, g, nact);
+        }
+    } else {
+        const int ra = 2 * warp, col = 2 + 2 * lane;
+        double2 cprev0 = make_double2(0.0, 0.0), cprev1 = cprev0, cc0 = cprev0, cc1 = cprev0;
+        double rz = 0.0;
+        int cur_a = -1;
+        double m_diag = 0.0, m_off = 0.0, pa = 0.0, pb = 0.0;
+        double* zp = nullptr;
+        double *z_lo = nullptr, *z_hi = nullptr;
+        while (c.valid) {
+            if (c.a != cur_a) {
+                if (cur_a >= 0) pipe_flush(sm, cur_a, rz);
+                cur_a = c.a;
+                rz = 0.0;
+                const int b = sm.act_list[c.a];
+                m_diag = s[b].m_diag;
+                m_off = s[b].m_off;
+                pa = s[b].pc_a;
+                pb = s[b].pc_b;
+                zp = s[b].z;
+                if (link != nullptr) {
+                    z_lo = link->has_lo ? link->lo_z_halo[b] : nullptr;
+                    z_hi = link->has_hi ? link->hi_z_halo[b] : nullptr;
+                }
+            }
+            const unsigned stg = k % kPipeStages;
+            mbar_wait(&sm.full[stg], (k / kPipeStages) & 1u);
+            const StageA& A = sm.st[stg].a;
+            const int x = c.x0 + 2 * lane, ya = c.y0 + ra;
+            const bool inx = x < P;
+            const double2 v0 = lds2(&A.R[1 + ra][col]), v1 = lds2(&A.R[2 + ra][col]);
+            if (NDIM == 2 || c.zp > c.z0) {
+                const StageA& A0 = NDIM == 3 ? sm.st[(k - 1u) % kPipeStages].a : A;
+                const double2 ca = NDIM == 3 ? cc0 : v0, cb = NDIM == 3 ? cc1 : v1;
+                const double2 up = lds2(&A0.R[ra][col]), dn = lds2(&A0.R[ra + 3][col]);
+                double la = __shfl_up_sync(0xffffffffu, ca.y, 1), ra_ = __shfl_down_sync(0xffffffffu, ca.x, 1);
+                double lb = __shfl_up_sync(0xffffffffu, cb.y, 1), rb_ = __shfl_down_sync(0xffffffffu, cb.x, 1);
+                if (lane == 0) {
+                    la = A0.R[1 + ra][1];
+                    lb = A0.R[2 + ra][1];
+                }
+                if (lane == 31 || x + 2 >= P) {
+                    if (x + 2 < P) {
+                        ra_ = A0.R[1 + ra][kPX + 2];
+                        rb_ = A0.R[2 + ra][kPX + 2];
+                    } else {
+                        ra_ = rb_ = 0.0;
+                    }
+                }
+                double2 nba = make_double2(la + ca.y, ca.x + ra_), nbb = make_double2(lb + cb.y, cb.x + rb_);
+                nba.x += up.x + cb.x;
+                nba.y += up.y + cb.y;
+                nbb.x += ca.x + dn.x;
+                nbb.y += ca.y + dn.y;
+                if (NDIM == 3) {
+                    nba.x += cprev0.x + v0.x;
+                    nba.y += cprev0.y + v0.y;
+                    nbb.x += cprev1.x + v1.x;
+                    nbb.y += cprev1.y + v1.y;
+                }
+                const long long idx = (NDIM == 3 ? (long long)(c.zp - 1) * g.sz : 0) + (long long)ya * g.sy + x;
+                const bool v0x = x < n, v1x = x + 1 < n;
+                double* push_lo = (NDIM == 3 && z_lo != nullptr && c.zp - 1 == 0) ? z_lo + (long long)ya * g.sy + x : nullptr;
+                double* push_hi = (NDIM == 3 && z_hi != nullptr && c.zp == g.nz) ? z_hi + (long long)ya * g.sy + x : nullptr;
+                if (inx && ya < n) {
+                    double2 z;
+                    z.x = v0x ? fma(pb, fma(m_off, nba.x, m_diag * ca.x), pa * ca.x) : 0.0;
+                    z.y = v1x ? fma(pb, fma(m_off, nba.y, m_diag * ca.y), pa * ca.y) : 0.0;
+                    st2(zp + idx, z);
+                    if (push_lo != nullptr) st2(push_lo, z);
+                    if (push_hi != nullptr) st2(push_hi, z);
+                    rz = fma(ca.x, z.x, rz);
+                    rz = fma(ca.y, z.y, rz);
+                }
+                if (inx && ya + 1 < n) {
+                    double2 z;
+                    z.x = v0x ? fma(pb, fma(m_off, nbb.x, m_diag * cb.x), pa * cb.x) : 0.0;
+                    z.y = v1x ? fma(pb, fma(m_off, nbb.y, m_diag * cb.y), pa * cb.y) : 0.0;
+                    st2(zp + idx + g.sy, z);
+                    if (push_lo != nullptr) st2(push_lo + g.sy, z);
+                    if (push_hi != nullptr) st2(push_hi + g.sy, z);
+                    rz = fma(cb.x, z.x, rz);
+                    rz = fma(cb.y, z.y, rz);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (NDIM == 3 && c.zp >= c.z0) mbar_arrive(&sm.empty[(k - 1u) % kPipeStages]);
+                if (NDIM == 2 || c.zp == c.z1) mbar_arrive(&sm.empty[stg]);
+            }
+            cprev0 = cc0;
+            cprev1 = cc1;
+            cc0 = v0;
+            cc1 = v1;
+            ++k;
+            cursor_next<NDIM>(c, U, g, nact);
+        }
+        if (cur_a >= 0) pipe_flush(sm, cur_a, rz);
+    }
+    kstep = k;
+    pipe_publish(sm, partials, 0);
 }
 
 }  // namespace sdcb200

@@ -68,9 +68,12 @@ class HeatMixin:
     forced = False
 
     def __init__(self, nvars=512, nu=0.1, freq=2, stencil_type="center", order=2, lintol=1e-12, liniter=10000,
-                 solver_type="direct", bc="periodic", sigma=6e-2, comm=None):
+                 solver_type="direct", bc="periodic", sigma=6e-2, comm=None, preconditioner=None):
         # `comm` is the one keyword the reference does not have (its FD problems are not space-parallel): a
-        # parallel.SlabComm decomposes the 3-D grid into slabs along axis 0, one per GPU; nvars stays the GLOBAL shape
+        # parallel.SlabComm decomposes the 3-D grid into slabs along axis 0, one per GPU; nvars stays the GLOBAL shape.
+        # `preconditioner='chebyshev'` (2-D / 3-D dirichlet-zero, CG) preconditions the node solves with a degree-1
+        # Chebyshev polynomial of the operator: same stopping test and tolerance as the reference's plain CG, about
+        # half the iterations (work_counters['CG'] then counts preconditioned iterations).
         # parameter checks of generic_ND_FD.py:99-133
         if type(nvars) not in [int, tuple]:
             raise ProblemError("nvars should be either tuple or int")
@@ -109,6 +112,10 @@ class HeatMixin:
         if solver_type == "direct" and ndim > 1:
             raise ProblemError("solver_type='direct' is implemented on the device for 1-D grids only; use 'CG'")
 
+        if preconditioner not in (None, "chebyshev"):
+            raise ProblemError(f"unknown preconditioner {preconditioner!r} (have None, 'chebyshev')")
+        if preconditioner is not None and (solver_type != "CG" or bc != "dirichlet-zero" or ndim < 2):
+            raise ProblemError("the polynomial preconditioner needs solver_type='CG' on a 2-D / 3-D dirichlet-zero grid")
         slab = comm is not None and hasattr(comm, "slab_layout")
         if slab and (ndim != 3 or solver_type != "CG" or bc != "dirichlet-zero"):
             raise ProblemError("slab-decomposed runs are implemented for 3-D dirichlet-zero grids with solver_type='CG'")
@@ -128,6 +135,7 @@ class HeatMixin:
         self.a_diag = ((-2.0 * ndim) / dx**2) * nu
         self._bc = BC_CODES[bc]
         self._be = get_backend()
+        self._precond = 1 if preconditioner == "chebyshev" else 0
         self._comm = comm if slab else None
         self._lay = comm.slab_layout(nvars) if slab else get_layout(nvars)
         self._counters = self._be.zeros(2 + 8, dtype=torch.int32)  # [total CG its, unused, per-system its of a solve]
@@ -224,10 +232,12 @@ class HeatMixin:
             work = self._cg_work(len(xs))
             self._comm.exchange_halos(xs)
             self._be.heat_cg_solve_slab(self._lay, self._comm, self._bc, m_diag, m_off, [r.flat for r in rhs],
-                                        [x.flat for x in xs], self.lintol, self.liniter, work, counters)
+                                        [x.flat for x in xs], self.lintol, self.liniter, work, counters,
+                                        precond=self._precond)
         else:
             self._be.heat_cg_solve(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs], [x.flat for x in xs],
-                                   self.lintol, self.liniter, self._cg_work(len(xs)), counters)
+                                   self.lintol, self.liniter, self._cg_work(len(xs)), counters,
+                                   precond=self._precond)
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, counters.clone()))

@@ -127,7 +127,7 @@ class NumpyBackend:
     def slab_cg_workspace(self, lay, comm, B):
         return None
 
-    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+    def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev, precond=0):
         """Distributed CG with the same structure as the device solver: halo exchange of the search direction, global
         dot products through the communicator; the halo planes of xs are valid on entry."""
         from pysdc_b200.comm import SUM
@@ -147,12 +147,21 @@ class NumpyBackend:
             r = bvec - (m_diag[b] * xfull[1:-1] + m_off[b] * self._slab_lap_sum(xfull, bc == 1))
             pfull_t = torch.zeros((nz + 2, lay.n, lay.n), dtype=torch.float64)
             pfull = pfull_t.numpy()
+            rfull_t = torch.zeros((nz + 2, lay.n, lay.n), dtype=torch.float64)
+            rfull = rfull_t.numpy()
+            cheb = self._cheb1(3, m_diag[b], m_off[b]) if precond else None
             rho_prev, its = None, 0
             for it in range(maxiter):
-                rho = dot(r, r)
-                if np.sqrt(rho) < atol:
+                if np.sqrt(dot(r, r)) < atol:
                     break
-                pfull[1:-1] = r if it == 0 else r + (rho / rho_prev) * pfull[1:-1]
+                if cheb is None:
+                    z = r
+                else:
+                    rfull[1:-1] = r
+                    comm.exchange_planes([(rfull_t[nz], rfull_t[0], rfull_t[1], rfull_t[nz + 1])], periodic=bc == 1)
+                    z = cheb[0] * r + cheb[1] * (m_diag[b] * r + m_off[b] * self._slab_lap_sum(rfull, bc == 1))
+                rho = dot(r, z)
+                pfull[1:-1] = z if it == 0 else z + (rho / rho_prev) * pfull[1:-1]
                 comm.exchange_planes([(pfull_t[nz], pfull_t[0], pfull_t[1], pfull_t[nz + 1])], periodic=bc == 1)
                 q = m_diag[b] * pfull[1:-1] + m_off[b] * self._slab_lap_sum(pfull, bc == 1)
                 alpha = rho / dot(pfull[1:-1], q)
@@ -206,8 +215,22 @@ class NumpyBackend:
 
     newton_workspace = lambda self, lay: torch.zeros(8, dtype=torch.float64)  # noqa: E731
 
-    def _cg(self, matvec, b, x, rtol, maxiter):
-        """scipy.sparse.linalg.cg's recurrence (atol = rtol*||b||, test before each iteration)."""
+    @staticmethod
+    def _cheb1(ndim, m_diag, m_off):
+        """Coefficients (a, b) of the degree-1 Chebyshev preconditioner z = a r + b M r (csrc/cg.cu::chebyshev1)."""
+        w = 2.0 * ndim * abs(m_off)
+        lmin, lmax = m_diag - w, m_diag + w
+        theta, delta = 0.5 * (lmax + lmin), 0.5 * (lmax - lmin)
+        if not delta > 0 or not lmin > 0:
+            return 1.0 / theta, 0.0
+        sigma = theta / delta
+        rho0 = 1.0 / sigma
+        rho1 = 1.0 / (2.0 * sigma - rho0)
+        return (1.0 + rho1 * rho0) / theta + 2.0 * rho1 / delta, -2.0 * rho1 / (delta * theta)
+
+    def _cg(self, matvec, b, x, rtol, maxiter, cheb=None):
+        """scipy.sparse.linalg.cg's recurrence (atol = rtol*||b||, test before each iteration), optionally
+        preconditioned with z = a r + b M r."""
         bnrm = np.linalg.norm(b)
         if bnrm == 0:
             x[...] = b
@@ -218,8 +241,9 @@ class NumpyBackend:
         for it in range(maxiter):
             if np.linalg.norm(r) < atol:
                 return its
-            rho = np.vdot(r, r)
-            p = r.copy() if it == 0 else r + (rho / rho_prev) * p
+            z = r if cheb is None else cheb[0] * r + cheb[1] * matvec(r)
+            rho = np.vdot(r, z)
+            p = z.copy() if it == 0 else z + (rho / rho_prev) * p
             q = matvec(p)
             alpha = rho / np.vdot(p, q)
             x += alpha * p
@@ -228,11 +252,12 @@ class NumpyBackend:
             its += 1
         return its
 
-    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev):
+    def heat_cg_solve(self, lay, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev, precond=0):
         self.launches += 1
         for b, (r, x) in enumerate(zip(rhs, xs)):
             mv = lambda v, b=b: m_diag[b] * v + m_off[b] * self._lap_sum(v, bc == 1)  # noqa: E731
-            iters_dev[b] += self._cg(mv, self._grid(lay, r).copy(), self._grid(lay, x), rtol, maxiter)
+            cheb = self._cheb1(lay.ndim, m_diag[b], m_off[b]) if precond else None
+            iters_dev[b] += self._cg(mv, self._grid(lay, r).copy(), self._grid(lay, x), rtol, maxiter, cheb)
 
     def heat_direct_solve_1d(self, lay, bc, m_diag, m_off, rhs, xs):
         self.launches += 1

@@ -50,6 +50,12 @@ def main():
     P.solve_system_batch([to_mesh(P, rhs_g) for _ in factors], factors, xs)
     sol_slab = [x.gather() for x in xs]
     cg_slab = P.work_counters["CG"].niter
+    # the same solves with the polynomial preconditioner (z halo planes travel through peer memory as well)
+    Pp = heatNd_unforced(**pp, comm=comm, preconditioner="chebyshev")
+    xp = [to_mesh(Pp, u_g) for _ in factors]
+    Pp.solve_system_batch([to_mesh(Pp, rhs_g) for _ in factors], factors, xp)
+    sol_pc = [x.gather() for x in xp]
+    cg_pc = Pp.work_counters["CG"].niter
 
     def run(pp_run):
         c = controller_nonMPI(1, {"logger_level": 40}, dict(
@@ -96,10 +102,13 @@ def main():
         checks = {"eval_f bitwise": bool(np.array_equal(f_slab, f_one)),
                   "solve vs 1 GPU": max(rel(a, b.get()) for a, b in zip(sol_slab, x1)),
                   "CG its slab / 1 GPU": (cg_slab, P1.work_counters["CG"].niter),
+                  "preconditioned solve vs 1 GPU": max(rel(a, b.get()) for a, b in zip(sol_pc, x1)),
+                  "preconditioned its": cg_pc,
                   "uend vs 1 GPU": rel(uend_slab, uend_one), "niter": (niter_slab, niter_one),
                   "imex uend vs 1 GPU": rel(uend_imex_slab, uend_imex_one), "imex niter": (niter_imex_slab, niter_imex_one)}
         ok = checks["eval_f bitwise"] and checks["solve vs 1 GPU"] < 1e-10 and checks["uend vs 1 GPU"] < 1e-10 \
             and niter_slab == niter_one and abs(cg_slab - P1.work_counters["CG"].niter) <= 4 \
+            and checks["preconditioned solve vs 1 GPU"] < 1e-10 and cg_pc < 0.8 * cg_slab \
             and checks["imex uend vs 1 GPU"] < 1e-10 and niter_imex_slab == niter_imex_one
         if n <= 63:
             import sdc_oracle

@@ -112,6 +112,49 @@ def test_stencil_and_cg_against_oracle(oracle, ndim, n, bc):
     assert pc.close_counts(P.work_counters["CG"].niter, O.counters["CG"].niter)
 
 
+@pytest.mark.parametrize("ndim,n", [(2, 63), (2, 127), (3, 33), (3, 65)])
+def test_polynomial_preconditioner(oracle, ndim, n):
+    """preconditioner='chebyshev': same solution as the reference's plain CG to the solver tolerance, about half the
+    iterations; SDC runs keep their iteration counts."""
+    from pysdc_b200.problems import heatNd_unforced
+
+    nvars, freq = (n,) * ndim, (2,) * ndim
+    kw = dict(nvars=nvars, nu=0.37, freq=freq, bc="dirichlet-zero", solver_type="CG", lintol=1e-12, liniter=500)
+    P0, P1 = heatNd_unforced(**kw), heatNd_unforced(**kw, preconditioner="chebyshev")
+    O = oracle.HeatFD(**kw)
+    rng = np.random.default_rng(7 * ndim + n)
+    u, rhs = rng.standard_normal(O.nvars), rng.standard_normal(O.nvars)
+    factor = 0.4 * O.dx_grid**2 / 0.37 * 40  # condition number ~ 1 + 4*ndim*16
+    ref = O.solve_system(rhs, factor, u, 0.0)
+    s0 = P0.solve_system(pc.to_mesh(P0, rhs), factor, pc.to_mesh(P0, u), 0.0).get()
+    s1 = P1.solve_system(pc.to_mesh(P1, rhs), factor, pc.to_mesh(P1, u), 0.0).get()
+    assert pc.relerr(s0, ref) < pc.TOL_SOLVE and pc.relerr(s1, ref) < pc.TOL_SOLVE
+    it0, it1 = P0.work_counters["CG"].niter, P1.work_counters["CG"].niter
+    assert 0.4 * it0 <= it1 <= 0.65 * it0, (it0, it1)
+    # batched launch with very different factors (per-system convergence inside the preconditioned loop)
+    factors = [factor * f for f in (0.02, 0.2, 1.0, 3.0)]
+    xb = [pc.to_mesh(P1, u) for _ in factors]
+    P1.solve_system_batch([pc.to_mesh(P1, rhs) for _ in factors], factors, xb)
+    for f, x in zip(factors, xb):
+        assert pc.relerr(x.get(), O.solve_system(rhs, f, u, 0.0)) < pc.TOL_SOLVE
+
+
+def test_preconditioned_sdc_run_keeps_iteration_counts():
+    spec, g = load_golden("run_heat3d_gi_minsrns_31")
+    d = pc.make_description(spec)
+    d["problem_params"] = dict(d["problem_params"], preconditioner="chebyshev")
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.stats import get_sorted
+
+    c = controller_nonMPI(1, {"logger_level": 40}, d)
+    P = c.MS[0].levels[0].prob
+    u0 = P.dtype_u(P.init)
+    u0[:] = np.random.default_rng(spec["seed"]).standard_normal(P.nvars)
+    uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+    assert [int(v) for _, v in get_sorted(stats, type="niter")] == g["niter"].tolist()
+    assert pc.relerr(uend.get(), g["uend"]) < pc.TOL_SOLVE
+
+
 def test_batched_solve_equals_sequential():
     """The node-batched launch must give each system exactly what a single-system launch gives (same reduction trees)."""
     from pysdc_b200.problems import heatNd_unforced

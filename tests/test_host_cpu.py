@@ -34,3 +34,23 @@ def test_run(name):
     # 1-D grids are badly conditioned (kappa ~ 1e4): CG loses orthogonality and its iteration count depends on
     # rounding details at the 10 % level; SDC iteration counts and the solution are unaffected
     pc.check_run(name, count_slack=None if "heat1d" in name else 0.02)
+
+
+def test_polynomial_preconditioner_host_semantics():
+    """Host side of preconditioner='chebyshev' (numpy test double): accepted only where it is implemented, same solution
+    as the plain solver, about half the iterations."""
+    from pysdc_b200.errors import ProblemError
+    from pysdc_b200.problems import heatNd_unforced
+
+    kw = dict(nvars=(31, 31), nu=0.37, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-12, liniter=500)
+    P0, P1 = heatNd_unforced(**kw), heatNd_unforced(**kw, preconditioner="chebyshev")
+    rng = np.random.default_rng(3)
+    u, rhs = rng.standard_normal((31, 31)), rng.standard_normal((31, 31))
+    s0 = P0.solve_system(pc.to_mesh(P0, rhs), 0.05, pc.to_mesh(P0, u), 0.0).get()
+    s1 = P1.solve_system(pc.to_mesh(P1, rhs), 0.05, pc.to_mesh(P1, u), 0.0).get()
+    assert pc.relerr(s1, s0) < 1e-10
+    assert 0.4 * P0.work_counters["CG"].niter <= P1.work_counters["CG"].niter <= 0.65 * P0.work_counters["CG"].niter
+    with pytest.raises(ProblemError):
+        heatNd_unforced(nvars=(32, 32), nu=0.1, freq=(2, 2), bc="periodic", solver_type="CG", preconditioner="chebyshev")
+    with pytest.raises(ProblemError):
+        heatNd_unforced(**dict(kw, preconditioner="jacobi"))

@@ -76,6 +76,23 @@ def _worker(rank, world, port, n, out_dir):
         hi = g[lay.z0 + lay.nz] if rank + 1 < world else np.zeros((n, n))
         assert np.array_equal(full[0], lo) and np.array_equal(full[-1], hi)
 
+        # preconditioned distributed solve == plain distributed solve (to the solver tolerance), fewer iterations
+        from pysdc_b200.problems import heatNd_unforced
+
+        kw = dict(_spec(n)["problem_params"], comm=comm)
+        Pa, Pb = heatNd_unforced(**kw), heatNd_unforced(**kw, preconditioner="chebyshev")
+        rhs_g = rng.standard_normal((n, n, n))
+
+        def solve(Pr):
+            b, x = Pr.dtype_u(Pr.init), Pr.dtype_u(Pr.init)
+            b[:] = rhs_g
+            x[:] = g
+            Pr.solve_system_batch([b], [2e-3], [x])
+            return x.gather(), Pr.work_counters["CG"].niter
+
+        (xa, ia), (xb_, ib) = solve(Pa), solve(Pb)
+        assert np.max(np.abs(xa - xb_)) / np.max(np.abs(xa)) < 1e-10 and ib < ia
+
         # a full SDC step on slabs == the single-process step
         u0 = np.random.default_rng(1234).standard_normal((n, n, n))
         uend, niter, P = _run_step(n, comm, u0)
