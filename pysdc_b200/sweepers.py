@@ -28,6 +28,29 @@ from .backend import get_backend
 from .errors import ParameterError
 
 
+class _LazyResiduals:
+    """``L.residual`` as the reference leaves it after ``compute_residual`` (core/sweeper.py:188-193: the M residual
+    fields), materialised only when somebody reads it: the sweep itself needs the max-norms only, and writing M more
+    fields per sweep would add a third to its streaming traffic."""
+
+    def __init__(self, sweeper):
+        self._sweeper, self._fields = sweeper, None
+
+    def _materialise(self):
+        if self._fields is None:
+            self._fields = self._sweeper._residual_fields()
+        return self._fields
+
+    def __getitem__(self, m):
+        return self._materialise()[m]
+
+    def __len__(self):
+        return self._sweeper.coll.num_nodes
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+
 class _SweepCommon:
     """Methods shared by both sweepers; ``self.coll / self.params / self.level / self.QI`` come from the base class."""
 
@@ -169,6 +192,8 @@ class _SweepCommon:
         if getattr(self.params, "store_residual", False):
             L.residual = [L.prob.dtype_u(L.prob.init) for _ in range(M)]
             res_out = [r.flat for r in L.residual]
+        else:
+            L.residual = _LazyResiduals(self)
         if "_resnorm" not in self.__dict__:
             self._resnorm = be.zeros(9)
         norms_dev = self._resnorm
@@ -197,6 +222,18 @@ class _SweepCommon:
                                  "last_rel instead")
         L.status.updated = False
         return None
+
+    def _residual_fields(self):
+        """The M residual fields of the level's current state (what the reference stores in ``L.residual``)."""
+        L = self.level
+        be = get_backend()
+        M = self.coll.num_nodes
+        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
+        taus = [None if t is None else t.flat for t in L.tau]
+        out = [L.prob.dtype_u(L.prob.init) for _ in range(M)]
+        be.colloc_residual(W, self._f_inputs(L), L.u[0].flat, [u.flat for u in L.u[1:]],
+                           taus if any(t is not None for t in taus) else None, [r.flat for r in out], be.zeros(M))
+        return out
 
     # ---- end point (generic_implicit.py:105-131, imex_1st_order.py:110-137) -----------------------------------------
     def compute_end_point(self):

@@ -129,6 +129,15 @@ def check_sweep_dump(name):
             # the residual is a difference of O(1) quantities each carrying the 1e-10 solve tolerance
             assert abs(L.status.residual - want) <= 1e-9 * max(abs(float(g["res_pred"])), 1.0), (rt, k)
         L.params.residual_type = "full_abs"
+        L.sweep.compute_residual()
+        # L.residual as the reference leaves it (core/sweeper.py:188-193): res[m] = integrate()[m] + u0 - u[m+1] (+ tau)
+        assert len(L.residual) == L.sweep.coll.num_nodes
+        for m, (res, q) in enumerate(zip(L.residual, integ)):
+            want = q + L.u[0] - L.u[m + 1]
+            if L.tau[m] is not None:
+                want += L.tau[m]
+            assert type(res) is P.dtype_u and abs(res - want) <= 1e-12 * max(1.0, abs(L.u[0]))
+        assert abs(max(abs(r) for r in L.residual) - L.status.residual) <= 1e-14 * max(1.0, L.status.residual)
         assert len(u_ids) == len(L.u)
         k += 1
     np.testing.assert_allclose(L.sweep.QI, g["QI"], rtol=0, atol=1e-14)
