@@ -38,7 +38,7 @@ def _description(name):
     return d, dict(spec["controller_params"]), spec["t0"], spec["Tend"], spec["num_procs"]
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, Tend_override=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -52,6 +52,7 @@ def _worker(rank, world, port, name, out_dir):
 
         backend.set_backend(NumpyBackend())
         d, cp, t0, Tend, _ = _description(name)
+        Tend = Tend if Tend_override is None else Tend_override
         c = controller_MPI(cp, d, comm=TorchComm())
         P = c.S.levels[0].prob
         uend, stats = c.run(u0=P.u_exact(t0), t0=t0, Tend=Tend)
@@ -129,5 +130,35 @@ def test_transfer_operators():
         R = np.kron(T.Rspace_1d, T.Rspace_1d)
         assert np.max(np.abs(T.restrict(u).get() - (R @ f0.ravel()).reshape(nc, nc))) < 1e-13
         assert np.allclose(T.Rspace_1d[3, 5:10], [0.0, 0.25, 0.5, 0.25, 0.0])
+    finally:
+        backend.set_backend(old)
+
+
+def test_partial_last_block_and_serial_mlsdc(tmp_path):
+    """6 time steps on 4 ranks: one full block and a last block of two slices (sub-communicator of the first two
+    ranks), compared with serial MLSDC through the same controller on a one-process communicator."""
+    name, world, Tend = "pfasst_heat2d_imex_63_p4", 4, 1.5
+    mp.spawn(_worker, args=(world, 29717, name, str(tmp_path), Tend), nprocs=world, join=True)
+    niter = []
+    for r in range(world):
+        niter += [tuple(x) for x in json.load(open(os.path.join(tmp_path, f"niter_{r}.json")))]
+    assert len(niter) == 6 and sorted(t for t, _ in niter) == pytest.approx([0.0, 0.25, 0.5, 0.75, 1.0, 1.25])
+    uend = np.load(os.path.join(tmp_path, "uend_0.npy"))  # ranks 0 and 1 hold the end value of the last block
+    assert np.array_equal(np.load(os.path.join(tmp_path, "uend_1.npy")), uend)
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_backend import NumpyBackend
+    from pysdc_b200 import backend
+    from pysdc_b200.pfasst import controller_MPI
+
+    old = backend._backend
+    backend.set_backend(NumpyBackend())
+    try:
+        d, cp, t0, _, _ = _description(name)
+        c = controller_MPI(cp, d)  # LocalComm: serial MLSDC
+        P = c.S.levels[0].prob
+        ref, stats = c.run(u0=P.u_exact(t0), t0=t0, Tend=Tend)
+        assert np.max(np.abs(uend - ref.get())) / np.max(np.abs(ref.get())) < 1e-7
+        assert abs(P.u_exact(Tend) - ref) < 5e-3  # second-order FD error of the 63^2 grid
     finally:
         backend.set_backend(old)
