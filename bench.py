@@ -127,10 +127,13 @@ def run_reference(args):
     n = args.ref_n
     t_all = time.perf_counter()
     rates = []
-    for _ in range(args.warmup):
+    # bounded: every step is ~10-25 s of single-core work; at most one untimed warm-up step and ~2.5 minutes in total
+    for _ in range(min(args.warmup, 1)):
         cpu_reference_rate(n, K_SWEEPS)
     for _ in range(max(args.steps, 1)):
         rates.append(cpu_reference_rate(n, K_SWEEPS))
+        if time.perf_counter() - t_all > 150.0:
+            break
     secs = sum(r["seconds"] for r in rates)
     value = n**3 * M_NODES * K_SWEEPS * len(rates) / secs
     sample = (f"oracle port of the reference path (scipy sparse matvec + scipy cg), same description at {n}^3 "
@@ -346,7 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=511, help="grid points per dimension (headline: 511)")
-    ap.add_argument("--ref-n", type=int, default=95, help="grid size of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=127, help="grid size of the bounded CPU sample (127^3: ~15 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", action="store_true", help="node solves with the polynomial preconditioner")
     args = ap.parse_args()
