@@ -53,13 +53,13 @@ __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, i
         }
         bb = block_sum(bb, sh.scratch);
         rr = block_sum(rr, sh.scratch);
-        put_partial(partials, 0, b, bb);
-        put_partial(partials, 1, b, rr);
+        put_partial(partials, kSlotSetup0, b, bb);
+        put_partial(partials, kSlotSetup1, b, rr);
     }
     grid_barrier(bar);
     for (int b = 0; b < B; ++b) {
-        const double bb = grid_sum(partials, 0, b, sh.scratch);
-        const double rr = grid_sum(partials, 1, b, sh.scratch);
+        const double bb = grid_sum(partials, kSlotSetup0, b, sh.scratch);
+        const double rr = grid_sum(partials, kSlotSetup1, b, sh.scratch);
         if (threadIdx.x == 0) {
             sh.bb[b] = bb;
             sh.rr[b] = rr;
@@ -124,12 +124,12 @@ __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, i
                     [&](long long idx, double2 c) { st2(p_new + idx, c); });
             }
             pq = block_sum(pq, sh.scratch);
-            put_partial(partials, 0, b, pq);
+            put_partial(partials, kSlotA, b, pq);
         }
         grid_barrier(bar);
         for (int b = 0; b < B; ++b) {
             if (!(act >> b & 1u)) continue;
-            const double pq = grid_sum(partials, 0, b, sh.scratch);
+            const double pq = grid_sum(partials, kSlotA, b, sh.scratch);
             if (threadIdx.x == 0) sh.alpha[b] = sh.rr[b] / pq;
         }
         __syncthreads();
@@ -157,12 +157,12 @@ __device__ void cg_collective(const Geom& g, int B, const Sys* s, double rtol, i
                 });
             }
             rr = block_sum(rr, sh.scratch);
-            put_partial(partials, 1, b, rr);
+            put_partial(partials, kSlotB, b, rr);
         }
         grid_barrier(bar);
         for (int b = 0; b < B; ++b) {
             if (!(act >> b & 1u)) continue;
-            const double rr = grid_sum(partials, 1, b, sh.scratch);
+            const double rr = grid_sum(partials, kSlotB, b, sh.scratch);
             if (threadIdx.x == 0) {
                 sh.rho_prev[b] = sh.rr[b];
                 sh.rr[b] = rr;
@@ -240,14 +240,14 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         }
         bb = block_sum(bb, sh.scratch);
         rr = block_sum(rr, sh.scratch);
-        put_partial(partials, 0, b, bb);
-        put_partial(partials, 1, b, rr);
+        put_partial(partials, kSlotSetup0, b, bb);
+        put_partial(partials, kSlotSetup1, b, rr);
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < B; ++b) {
-            r_slots[2 * b] = 0;
+            r_slots[2 * b] = kSlotSetup0;
             r_sys[2 * b] = b;
-            r_slots[2 * b + 1] = 1;
+            r_slots[2 * b + 1] = kSlotSetup1;
             r_sys[2 * b + 1] = b;
         }
     }
@@ -280,7 +280,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
                 if (sh.active >> b & 1u) {
                     sm.act_list[na] = b;
                     r_sys[na] = b;
-                    r_slots[na] = 0;
+                    r_slots[na] = kSlotC;
                     ++na;
                 }
             sm.nact = na;
@@ -328,7 +328,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         // ---- phase A ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
         pipe_phase_a<NDIM>(g, PU, s, maps, it == 0, cur, sh, sm, partials, kstep);
-        if (threadIdx.x < nact) r_slots[threadIdx.x] = 0;
+        if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotA;
         fence_proxy_async_global();
         reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
         if ((int)threadIdx.x < nact) sh.alpha[r_sys[threadIdx.x]] = sh.rz[r_sys[threadIdx.x]] / sh.glob[threadIdx.x];
@@ -337,7 +337,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         // ---- phase B ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
         pipe_phase_b<NDIM>(g, PU, s, maps, cur, sh, sm, partials, kstep, link);
-        if (threadIdx.x < nact) r_slots[threadIdx.x] = 1;
+        if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotB;
         fence_proxy_async_global();
         reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
         if ((int)threadIdx.x < nact) {
@@ -360,13 +360,14 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
                     if (sqrt(sh.rr[b]) < rtol * sqrt(sh.bb[b]) || it + 1 >= maxiter) continue;
                     sm.act_list[na] = b;
                     r_sys[na] = b;
-                    r_slots[na] = 0;
+                    r_slots[na] = kSlotC;
                     ++na;
                 }
                 sm.nact = na;
             }
             __syncthreads();
             const int nc = sm.nact;
+            __syncthreads();  // everybody holds nc before thread 0 may rewrite the list at the top of the loop
             if (nc > 0) {
                 fence_proxy_async_global();
                 pipe_phase_c<NDIM>(g, PU, s, maps, sm, partials, kstep, link);
@@ -466,12 +467,12 @@ __global__ void __launch_bounds__(kThreads) newton_kernel(const __grid_constant_
             });
         }
         gmax = block_max(gmax, sh.scratch);
-        put_partial(a.partials, 0, 0, gmax);
+        put_partial(a.partials, kSlotC, 0, gmax);
         grid_barrier(a.bar);
-        const double res = grid_max(a.partials, 0, 0, sh.scratch);
+        const double res = grid_max(a.partials, kSlotC, 0, sh.scratch);
         if (a.inexact_ratio > 0.0) lin_tol = res * a.inexact_ratio;
         if (res < a.newton_tol) break;
-        grid_barrier(a.bar);  // everybody has read partials slot 0 before the CG reuses it
+        grid_barrier(a.bar);  // everybody has read the residual norm before anybody can come back here and rewrite it
 
         cg_collective<2, true>(g, 1, &sys, lin_tol, a.lin_maxiter, a.partials, a.bar, sh);
         if (threadIdx.x == 0) {
@@ -525,7 +526,7 @@ WorkLayout work_layout(int ndim, int n, int nfields) {
     w.guard_bytes = guard * sizeof(double);
     w.field = align_up((guard + vol) * sizeof(double), 256);
     w.partials_off = 0;
-    w.bar_off = align_up(2 * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
+    w.bar_off = align_up(kPartialSlots * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
     w.fields_off = w.bar_off + 256;
     w.total = w.fields_off + (size_t)nfields * w.field;
     return w;
@@ -544,7 +545,7 @@ SlabWorkLayout slab_work_layout(int n, int nz_max, int nfields) {
     w.guard_bytes = guard * sizeof(double);
     w.field = align_up((guard + sz * (size_t)(nz_max + 1)) * sizeof(double), 256);
     w.partials_off = 0;
-    w.bar_off = align_up(2 * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
+    w.bar_off = align_up(kPartialSlots * SDCB200_MAX_NODES * kMaxGrid * sizeof(double), 256);
     w.seq_off = w.bar_off + 256;
     w.err_off = w.seq_off + 128;
     w.flags_off = w.seq_off + 256;

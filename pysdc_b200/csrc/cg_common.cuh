@@ -67,6 +67,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar) {
     __syncthreads();
 }
 
+// Per-CTA partial sums live in kPartialSlots areas of [MAX_NODES][gridDim.x] doubles.  A slot may only be rewritten
+// after a grid barrier that every CTA enters AFTER its last read of the slot, so consecutive reductions never share a
+// slot: pass A uses 0, pass B 1, pass C (preconditioner) 2, the set-up pass 3 and 4 (written once per solve).
+constexpr int kPartialSlots = 5;
+enum { kSlotA = 0, kSlotB = 1, kSlotC = 2, kSlotSetup0 = 3, kSlotSetup1 = 4 };
+
 // Sum the per-CTA partials of one quantity in a fixed order; identical bits in every thread of every CTA.
 __device__ __forceinline__ double grid_sum(const double* partials, int slot, int b, double* scratch) {
     const double* src = partials + (size_t)(slot * SDCB200_MAX_NODES + b) * gridDim.x;

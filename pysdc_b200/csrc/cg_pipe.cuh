@@ -394,7 +394,7 @@ __device__ void pipe_phase_a(const Geom& g, const PUnits& U, const Sys* s, const
         if (cur_a >= 0) pipe_flush(sm, cur_a, pq);
     }
     kstep = k;
-    pipe_publish(sm, partials, 0);
+    pipe_publish(sm, partials, kSlotA);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -533,7 +533,7 @@ __device__ void pipe_phase_b(const Geom& g, const PUnits& U, const Sys* s, const
         if (cur_a >= 0) pipe_flush(sm, cur_a, rr);
     }
     kstep = k;
-    pipe_publish(sm, partials, 1);
+    pipe_publish(sm, partials, kSlotB);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -661,7 +661,7 @@ __device__ void pipe_phase_c(const Geom& g, const PUnits& U, const Sys* s, const
         if (cur_a >= 0) pipe_flush(sm, cur_a, rz);
     }
     kstep = k;
-    pipe_publish(sm, partials, 0);
+    pipe_publish(sm, partials, kSlotC);
 }
 
 }  // namespace sdcb200
