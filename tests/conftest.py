@@ -32,3 +32,12 @@ def oracle():
     import sdc_oracle
 
     return sdc_oracle
+
+
+def free_port():
+    """A TCP port that is free right now on 127.0.0.1 (rendezvous of the multi-process gloo tests)."""
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sock:
+        sock.bind(("127.0.0.1", 0))
+        return sock.getsockname()[1]

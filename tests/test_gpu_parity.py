@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import parity_cases as pc
-from conftest import golden_names, load_golden
+from conftest import free_port, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -313,7 +313,7 @@ def test_slab_decomposed_run_on_two_gpus():
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu", "slab_check.py"), "63"]
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(root, "tests", "mgpu", "slab_check.py"), "63"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "slab_check n=63 world=2: OK" in res.stdout
@@ -330,7 +330,7 @@ def test_pfasst_time_slices(name, world):
     transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-           "127.0.0.1", "--master-port", str(29540 + world), os.path.join(root, "tests", "mgpu", "pfasst_check.py"),
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(root, "tests", "mgpu", "pfasst_check.py"),
            name, transport]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]

@@ -9,7 +9,7 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, free_port, load_golden
 
 REF = os.environ.get("PYSDC_REFERENCE", "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pySDC")), reason="reference tree not present")
@@ -59,7 +59,7 @@ def _worker(rank, world, port, name, out_dir):
 def test_reference_controller_MPI_on_the_facade(tmp_path):
     name, world = "pfasst_heat2d_imex_63_p4", 4
     _, g = load_golden(name)
-    mp.spawn(_worker, args=(world, 29731, name, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, free_port(), name, str(tmp_path)), nprocs=world, join=True)
     niter = []
     for r in range(world):
         niter += [tuple(x) for x in json.load(open(os.path.join(tmp_path, f"niter_{r}.json")))]

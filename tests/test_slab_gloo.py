@@ -105,7 +105,9 @@ def _worker(rank, world, port, n, out_dir):
 
 @pytest.mark.parametrize("world,n", [(2, 15), (3, 13)])
 def test_slab_step_matches_serial(tmp_path, world, n):
-    port = 29600 + world * 7 + n
+    from conftest import free_port
+
+    port = free_port()
     mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
