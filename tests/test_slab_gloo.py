@@ -41,6 +41,25 @@ def _run_step(n, comm, u0_global):
     return uend, niter, P
 
 
+def _run_imex(n, comm):
+    """Forced heat, IMEX sweeper with LU (sequential node solves) - the multi-component datatype on slabs."""
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.problems import heatNd_forced
+    from pysdc_b200.stats import get_sorted
+    from pysdc_b200.sweepers import imex_1st_order
+
+    pp = dict(_spec(n)["problem_params"], freq=(2, 2, 2))
+    if comm is not None:
+        pp["comm"] = comm
+    c = controller_nonMPI(1, {"logger_level": 40}, dict(
+        problem_class=heatNd_forced, problem_params=pp, sweeper_class=imex_1st_order,
+        sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+        level_params=dict(dt=5e-3, restol=1e-9), step_params=dict(maxiter=50)))
+    P = c.MS[0].levels[0].prob
+    uend, stats = c.run(u0=P.u_exact(0.0), t0=0.0, Tend=1e-2)
+    return uend, [v for _, v in get_sorted(stats, type="niter")], P
+
+
 def _worker(rank, world, port, n, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -99,6 +118,10 @@ def _worker(rank, world, port, n, out_dir):
         np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.gather())
         np.save(os.path.join(out_dir, f"niter_{rank}.npy"), np.array(niter))
         np.save(os.path.join(out_dir, f"cg_{rank}.npy"), np.array(P.work_counters["CG"].niter))
+        uend, niter, P = _run_imex(n, comm)
+        assert abs(P.u_exact(1e-2) - uend) < 0.05  # global max-norm through the communicator
+        np.save(os.path.join(out_dir, f"imex_uend_{rank}.npy"), uend.gather())
+        np.save(os.path.join(out_dir, f"imex_niter_{rank}.npy"), np.array(niter))
     finally:
         dist.destroy_process_group()
 
@@ -127,6 +150,12 @@ def test_slab_step_matches_serial(tmp_path, world, n):
             assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
             assert list(np.load(os.path.join(tmp_path, f"niter_{r}.npy"))) == niter
             assert abs(int(np.load(os.path.join(tmp_path, f"cg_{r}.npy"))) - P.work_counters["CG"].niter) <= 2
+        uend, niter, _ = _run_imex(n, None)
+        ref = uend.get()
+        for r in range(world):
+            got = np.load(os.path.join(tmp_path, f"imex_uend_{r}.npy"))
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+            assert list(np.load(os.path.join(tmp_path, f"imex_niter_{r}.npy"))) == niter
     finally:
         backend.set_backend(old)
         mesh.comm = old_comm
