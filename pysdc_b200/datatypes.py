@@ -164,6 +164,11 @@ class mesh:
 
     numpy = get
 
+    def view(self, cls=None):
+        """``u.view(numpy.ndarray)`` as used by the reference's output hooks (hooks/log_solution.py:109-110): a host
+        copy of the grid values (the device field itself cannot be re-typed)."""
+        return self.get()
+
     def __array__(self, dtype=None, copy=None):
         a = self.get()
         return a if dtype is None else a.astype(dtype)
