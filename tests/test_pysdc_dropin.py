@@ -88,3 +88,33 @@ def test_reference_pfasst_controller_drives_plugin_classes(plugin):
     niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
     assert niter == g["niter"].tolist()
     assert np.max(np.abs(uend.get() - g["uend"])) / np.max(np.abs(g["uend"])) < 1e-10
+
+
+def test_reference_hooks_work_on_device_fields(plugin):
+    """The reference's logging hooks (solution, work, iteration counts, step size, timings, errors against u_exact) read
+    L.uend / L.u / L.status / work_counters of the plug-in classes without modification."""
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+    from pySDC.implementations.hooks.log_errors import LogGlobalErrorPostRun, LogLocalErrorPostStep
+    from pySDC.implementations.hooks.log_solution import LogSolution
+    from pySDC.implementations.hooks.log_step_size import LogStepSize
+    from pySDC.implementations.hooks.log_timings import CPUTimings
+    from pySDC.implementations.hooks.log_work import LogSDCIterations, LogWork
+
+    hooks = [LogSolution, LogWork, LogSDCIterations, LogStepSize, CPUTimings, LogGlobalErrorPostRun,
+             LogLocalErrorPostStep]
+    d = dict(problem_class=plugin.heatNd_unforced,
+             problem_params=dict(nvars=(15, 15), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-12,
+                                 liniter=1000),
+             sweeper_class=plugin.generic_implicit, sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+             level_params=dict(dt=0.01, restol=1e-9), step_params=dict(maxiter=20))
+    c = controller_nonMPI(num_procs=1, controller_params=dict(logger_level=40, hook_class=hooks), description=d)
+    P = c.MS[0].levels[0].prob
+    uend, stats = c.run(u0=P.u_exact(0.0), t0=0.0, Tend=0.03)
+    sols = get_sorted(stats, type="u", sortby="time")
+    assert len(sols) == 3 and type(sols[-1][1]) is plugin.mesh
+    assert np.array_equal(sols[-1][1].get(), uend.get())
+    assert sum(v for _, v in get_sorted(stats, type="work_CG")) == P.work_counters["CG"].niter
+    assert [v for _, v in get_sorted(stats, type="k")] == [v for _, v in get_sorted(stats, type="niter")]
+    err = get_sorted(stats, type="e_global_post_run")[-1][1]
+    assert err == pytest.approx(abs(P.u_exact(0.03) - uend)) and err < 1e-3
