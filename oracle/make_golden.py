@@ -327,6 +327,36 @@ def operator_vectors():
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# space transfer: the reference's mesh_to_mesh (sparse Kronecker products) applied to seeded random fields
+# ----------------------------------------------------------------------------------------------------------------
+def transfer_vectors():
+    rng = np.random.default_rng(77)
+    cases = [
+        ("1d_dirichlet", heatNd_unforced, dict(nu=0.1, freq=2, bc="dirichlet-zero"), 63, 31, dict(rorder=2, iorder=6)),
+        ("2d_dirichlet", heatNd_forced, dict(nu=0.1, freq=(2, 2), bc="dirichlet-zero"), (31, 31), (15, 15), dict(rorder=2, iorder=6)),
+        ("2d_dirichlet_o4", heatNd_unforced, dict(nu=0.1, freq=(2, 2), bc="dirichlet-zero"), (31, 31), (15, 15), dict(rorder=2, iorder=4)),
+        ("3d_dirichlet", heatNd_unforced, dict(nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero"), (15, 15, 15), (7, 7, 7), dict(rorder=2, iorder=2)),
+        ("2d_periodic", heatNd_unforced, dict(nu=0.1, freq=(2, 2), bc="periodic"), (32, 32), (16, 16), dict(rorder=2, iorder=6, periodic=True)),
+        ("1d_periodic", heatNd_unforced, dict(nu=0.1, freq=2, bc="periodic"), 64, 32, dict(rorder=2, iorder=4, periodic=True)),
+    ]
+    for tag, cls, pp, nf, nc, tp in cases:
+        Pf, Pc = cls(nvars=nf, **pp), cls(nvars=nc, **pp)
+        T = mesh_to_mesh(Pf, Pc, tp)
+        F, G = Pf.u_init, Pc.u_init
+        F[:] = rng.standard_normal(F.shape)
+        G[:] = rng.standard_normal(G.shape)
+        out = dict(F=np.asarray(F), G=np.asarray(G), RF=np.asarray(T.restrict(F)), PG=np.asarray(T.prolong(G)))
+        if cls is heatNd_forced:  # multi-component right-hand sides go through component by component
+            Ff, Gf = Pf.f_init, Pc.f_init
+            Ff[:] = rng.standard_normal(Ff.shape)
+            Gf[:] = rng.standard_normal(Gf.shape)
+            out.update(Ff=np.asarray(Ff), Gf=np.asarray(Gf), RFf=np.asarray(T.restrict(Ff)), PGf=np.asarray(T.prolong(Gf)))
+        spec = dict(problem=cls.__name__, problem_params=_jsonable(pp), nvars_fine=_jsonable(dict(n=nf))["n"],
+                    nvars_coarse=_jsonable(dict(n=nc))["n"], transfer_params=tp)
+        save("transfer_" + tag, spec, **out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # PFASST (config 5 scaled down) through the reference's virtual-parallel controller
 # ----------------------------------------------------------------------------------------------------------------
 def pfasst_runs():
@@ -413,7 +443,8 @@ def pfasst_config5():
     print("  PFASST config 5", niter, "wall", wall)
 
 
-FAMILIES = {"runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "pfasst": pfasst_runs,
+FAMILIES = {"runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "transfer": transfer_vectors,
+            "pfasst": pfasst_runs,
             "pfasst_config5": pfasst_config5}
 
 if __name__ == "__main__":

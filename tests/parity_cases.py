@@ -188,3 +188,29 @@ def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
         elif count_slack is not None:
             assert close_counts(got, want, count_slack), (key, got, want)
     return dict(niter=niter, uend=uend, stats=stats)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def check_transfer(name):
+    """mesh_to_mesh restriction / prolongation vs the reference's sparse Kronecker-product operators
+    (transfer_classes/TransferMesh.py:149-218) on the fixture's seeded fields."""
+    from pysdc_b200.transfer import mesh_to_mesh
+
+    spec, g = load_golden(name)
+    probs, _ = classes()
+    pp = tuplify(spec["problem_params"])
+    as_nvars = lambda v: tuple(v) if isinstance(v, list) else v  # noqa: E731
+    Pf = probs[spec["problem"]](nvars=as_nvars(spec["nvars_fine"]), solver_type="CG", **pp)
+    Pc = probs[spec["problem"]](nvars=as_nvars(spec["nvars_coarse"]), solver_type="CG", **pp)
+    T = mesh_to_mesh(Pf, Pc, dict(spec["transfer_params"]))
+    F, G = to_mesh(Pf, g["F"]), to_mesh(Pc, g["G"])
+    RF, PG = T.restrict(F), T.prolong(G)
+    assert type(RF) is Pc.dtype_u and type(PG) is Pf.dtype_u
+    assert RF.shape == g["RF"].shape and PG.shape == g["PG"].shape
+    assert relerr(RF.get(), g["RF"]) < TOL_ARITH and relerr(PG.get(), g["PG"]) < TOL_ARITH
+    assert np.array_equal(F.get(), g["F"]) and np.array_equal(G.get(), g["G"])  # inputs untouched
+    if "Ff" in g:
+        Ff, Gf = to_mesh(Pf, g["Ff"], Pf.dtype_f), to_mesh(Pc, g["Gf"], Pc.dtype_f)
+        RFf, PGf = T.restrict(Ff), T.prolong(Gf)
+        assert type(RFf) is Pc.dtype_f and type(PGf) is Pf.dtype_f
+        assert relerr(RFf.get(), g["RFf"]) < TOL_ARITH and relerr(PGf.get(), g["PGf"]) < TOL_ARITH

@@ -24,6 +24,11 @@ def test_operator(name):
     pc.check_operator(name)
 
 
+@pytest.mark.parametrize("name", golden_names("transfer_"))
+def test_transfer(name):
+    pc.check_transfer(name)
+
+
 @pytest.mark.parametrize("name", golden_names("sweep_"))
 def test_sweep_dump(name):
     pc.check_sweep_dump(name)
