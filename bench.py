@@ -273,10 +273,10 @@ def run_b200(args):
         W = np.random.default_rng(0).standard_normal((M_NODES, len(fins)))
         norms = be.zeros(M_NODES)
         kernels = {
-            "colloc_apply_kernel<4> (rhs assembly: u0 + dt(Q-QD)F)":
-                (lambda: be.colloc_apply(W, fins, L.u[0].flat, None, [r.flat for r in rhs]), 8 * (2 * M_NODES + 1)),
-            "colloc_residual_kernel<4> (residual + max-norms)":
-                (lambda: be.colloc_residual(W, fins, L.u[0].flat, [u.flat for u in L.u[1:]], None, None, norms),
+            "colloc_sweep_kernel<4,1> (rhs assembly: u0 + dt(Q-QD)F)":
+                (lambda: be.colloc_sweep(fins, 1, [r.flat for r in rhs], Wq=W, Wi=-W, base=L.u[0].flat), 8 * (2 * M_NODES + 1)),
+            "colloc_residual_kernel<4,1> (residual + max-norms)":
+                (lambda: be.colloc_residual(W, fins, 1, L.u[0].flat, [u.flat for u in L.u[1:]], None, None, norms),
                  8 * (2 * M_NODES + 1)),
             "eval_f_kernel<3> (4 fields)":
                 (lambda: P.eval_f_batch(L.u[1:], [0.0] * M_NODES, L.f[1:]), 16 * M_NODES),

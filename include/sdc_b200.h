@@ -58,19 +58,46 @@ int sdcb200_maxabs(const double* x, long long count, double* out_dev, void* stre
 int sdcb200_axpby(long long count, double a, const double* x, double b, const double* y, double* out, void* stream);
 
 /* ---- K1: collocation --------------------------------------------------------------------------------------------
- * out[m] = (base ? base : 0) + sum_k W[m*nin + k] * in[k] + (add && add[m] ? add[m] : 0),   m < nout, k < nin
- * One coalesced, double2-vectorised pass: every input is read once, every output written once.
- * Replaces the M^2 axpy loops of generic_implicit.integrate (generic_implicit.py:29-49), the "known terms" loop of
- * update_nodes (generic_implicit.py:70-82, imex_1st_order.py:77-88: W = dt*(Q - QI) [and dt*(Q - QE)]), the new-node
- * rhs additions (generic_implicit.py:87-89) and compute_end_point (generic_implicit.py:123-129).                   */
+ * out[m] = sum_k W[m*nin + k] * in[k] (k ascending, products and sums rounded separately) + (base ? base : 0)
+ *          + (add && add[m] ? add[m] : 0),   m < nout, k < nin
+ * One coalesced, double2-vectorised pass: every input is read once, every output written once.  Generic linear
+ * combination of fields: the node-to-node combinations of the FAS transfer (core/base_transfer.py:93-251).          */
 int sdcb200_colloc_apply(long long count, int nout, int nin, const double* W_host,
                          const double* const* in, const double* base, const double* const* add,
                          double* const* out, void* stream);
 
-/* res[m] = sum_k W[m*nin+k]*in[k] + (u0 - u[m]) + tau[m];  resnorm_dev[m] = max|res[m]|  (device, M doubles).
- * res_out may be NULL (norm only, nothing written) or an array of M device pointers.
+/* The node combinations of one SDC sweep in the reference's OWN order of floating-point operations (every product and
+ * sum rounded separately, no FMA contraction), so that they reproduce numpy bit for bit:
+ *
+ *   acc[m] = BASE_FIRST ? base : 0
+ *   QUADRATURE:  for j < nj:  acc[m] += Wq[m*nj+j] * F_j        F_j = in[j]               (ncomp == 1, mesh)
+ *                                                                F_j = in[2j] + in[2j+1]   (ncomp == 2, imex_mesh:
+ *                                                                                           f[j].impl + f[j].expl)
+ *   QDELTA:      for j < nj:  acc[m] += Wi[m*nj+j] * in[j]                                  (ncomp == 1)
+ *                             acc[m] += dt2 * (Wi[m*nj+j]*in[2j] + We[m*nj+j]*in[2j+1])     (ncomp == 2)
+ *   if !BASE_FIRST and base:  acc[m] += base
+ *   if add && add[m]:         acc[m] += add[m]                                              (tau)
+ *   out[m] = acc[m]                                                    m < nout; out[m] may alias base
+ *
+ * - integrate (generic_implicit.py:29-49, imex_1st_order.py:37-55): QUADRATURE with Wq = dt*Q.
+ * - known terms of update_nodes (generic_implicit.py:70-82): QUADRATURE | QDELTA with Wq = dt*Q, Wi = -(dt*QI), base =
+ *   u[0], add = tau; IMEX (imex_1st_order.py:77-88): Wi = -QI, We = -QE, dt2 = dt (negation is exact, so
+ *   `integral -= dt*(QI f.impl + QE f.expl)` is reproduced).
+ * - new-node additions (generic_implicit.py:87-89, imex_1st_order.py:92-95): BASE_FIRST | QDELTA on rhs[m] in place.
+ * - compute_end_point (generic_implicit.py:123-129, imex_1st_order.py:128-135): BASE_FIRST | QUADRATURE with
+ *   Wq = dt*weights, base = u[0], add = tau[-1].
+ * One coalesced double2 pass; the second read of in[] in the QDELTA phase is served by L1/L2.                        */
+#define SDCB200_SWEEP_QUADRATURE 1
+#define SDCB200_SWEEP_QDELTA 2
+#define SDCB200_SWEEP_BASE_FIRST 4
+int sdcb200_colloc_sweep(long long count, int nout, int nj, int ncomp, int flags, const double* Wq_host,
+                         const double* Wi_host, const double* We_host, double dt2, const double* const* in,
+                         const double* base, const double* const* add, double* const* out, void* stream);
+
+/* res[m] = sum_j Wq[m*nj+j]*F_j + (u0 - u[m]) + tau[m];  resnorm_dev[m] = max|res[m]|  (device, M doubles); F_j as in
+ * sdcb200_colloc_sweep.  res_out may be NULL (norm only, nothing written) or an array of M device pointers.
  * Replaces Sweeper.compute_residual (core/sweeper.py:164-215) incl. the max-norm of mesh.__abs__.                 */
-int sdcb200_colloc_residual(long long count, int M, int nin, const double* W_host,
+int sdcb200_colloc_residual(long long count, int M, int nj, int ncomp, const double* Wq_host,
                             const double* const* in, const double* u0, const double* const* u,
                             const double* const* tau, double* const* res_out, double* resnorm_dev, void* stream);
 

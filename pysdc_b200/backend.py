@@ -37,7 +37,8 @@ def _declare(lib):
         "sdcb200_maxabs": (c_int, [_c_dp, c_ll, _c_dp, _c_dp]),
         "sdcb200_axpby": (c_int, [c_ll, c_d, _c_dp, c_d, _c_dp, _c_dp, _c_dp]),
         "sdcb200_colloc_apply": (c_int, [c_ll, c_int, c_int, PD, PP, _c_dp, PP, PP, _c_dp]),
-        "sdcb200_colloc_residual": (c_int, [c_ll, c_int, c_int, PD, PP, _c_dp, PP, PP, PP, _c_dp, _c_dp]),
+        "sdcb200_colloc_sweep": (c_int, [c_ll, c_int, c_int, c_int, c_int, PD, PD, PD, c_d, PP, _c_dp, PP, PP, _c_dp]),
+        "sdcb200_colloc_residual": (c_int, [c_ll, c_int, c_int, c_int, PD, PP, _c_dp, PP, PP, PP, _c_dp, _c_dp]),
         "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
@@ -144,11 +145,26 @@ class CudaBackend:
             None if base is None else base.data_ptr(), None if adds is None else _ptr_array(adds),
             _ptr_array(outs), self._stream()))
 
-    def colloc_residual(self, W, ins, u0, us, taus, res_outs, resnorm):
-        W = np.asarray(W, dtype=np.float64).reshape(len(us), len(ins))
+    def colloc_sweep(self, ins, ncomp, outs, Wq=None, Wi=None, We=None, dt2=0.0, base=None, adds=None,
+                     base_first=False):
+        """The node combinations of a sweep in the reference's order of operations (sdc_b200.h: sdcb200_colloc_sweep).
+        ``ins`` = f[j] per node (ncomp = 1) or f[j].impl, f[j].expl interleaved (ncomp = 2); ``Wq`` (nout x nj) the
+        quadrature phase, ``Wi`` / ``We`` the QDelta phase."""
+        nj = len(ins) // ncomp
+        flags = (1 if Wq is not None else 0) | (2 if Wi is not None else 0) | (4 if base_first else 0)
+        arr = lambda W: None if W is None else _dbl_array(np.asarray(W, dtype=np.float64).reshape(len(outs), nj))  # noqa: E731
+        self.launches += 1
+        self._check(self.lib.sdcb200_colloc_sweep(
+            outs[0].numel(), len(outs), nj, ncomp, flags, arr(Wq), arr(Wi), arr(We), float(dt2), _ptr_array(ins),
+            None if base is None else base.data_ptr(), None if adds is None else _ptr_array(adds), _ptr_array(outs),
+            self._stream()))
+
+    def colloc_residual(self, Wq, ins, ncomp, u0, us, taus, res_outs, resnorm):
+        nj = len(ins) // ncomp
+        Wq = np.asarray(Wq, dtype=np.float64).reshape(len(us), nj)
         self.launches += 1
         self._check(self.lib.sdcb200_colloc_residual(
-            u0.numel(), len(us), len(ins), _dbl_array(W), _ptr_array(ins), u0.data_ptr(), _ptr_array(us),
+            u0.numel(), len(us), nj, ncomp, _dbl_array(Wq), _ptr_array(ins), u0.data_ptr(), _ptr_array(us),
             None if taus is None else _ptr_array(taus), None if res_outs is None else _ptr_array(res_outs),
             resnorm.data_ptr(), self._stream()))
 

@@ -21,7 +21,20 @@ struct CollocArgs {
     int nin;
 };
 
-// out[m] = base + sum_k W[m][k] in[k] + add[m]
+// Rounding: every product and every sum is rounded on its own (__dmul_rn / __dadd_rn are never contracted into an FMA)
+// and the terms are accumulated in ascending k starting from 0, which is what the reference's loops
+// `me[-1] += L.dt * self.coll.Qmat[m, j] * L.f[j]` (generic_implicit.py:46-47) do with numpy: scalar coefficient
+// first, one rounded product, one rounded sum per term.
+__device__ __forceinline__ void mul_add(double2& acc, double w, const double2 v) {
+    acc.x = __dadd_rn(acc.x, __dmul_rn(w, v.x));
+    acc.y = __dadd_rn(acc.y, __dmul_rn(w, v.y));
+}
+__device__ __forceinline__ void add2(double2& acc, const double2 v) {
+    acc.x = __dadd_rn(acc.x, v.x);
+    acc.y = __dadd_rn(acc.y, v.y);
+}
+
+// out[m] = sum_k W[m][k] in[k] + base + add[m]   (generic linear combination)
 template <int NOUT>
 __global__ void __launch_bounds__(kThreads) colloc_apply_kernel(const __grid_constant__ CollocArgs a) {
     const long long stride = (long long)gridDim.x * kThreads;
@@ -33,35 +46,100 @@ __global__ void __launch_bounds__(kThreads) colloc_apply_kernel(const __grid_con
         for (int k = 0; k < a.nin; ++k) {
             const double2 v = ld2(a.in[k] + 2 * i);
 #pragma unroll
-            for (int m = 0; m < NOUT; ++m) {
-                const double w = a.W[m * a.nin + k];
-                acc[m].x = fma(w, v.x, acc[m].x);
-                acc[m].y = fma(w, v.y, acc[m].y);
-            }
+            for (int m = 0; m < NOUT; ++m) mul_add(acc[m], a.W[m * a.nin + k], v);
         }
         if (a.base != nullptr) {
             const double2 b = ld2(a.base + 2 * i);
 #pragma unroll
-            for (int m = 0; m < NOUT; ++m) {
-                acc[m].x += b.x;
-                acc[m].y += b.y;
-            }
+            for (int m = 0; m < NOUT; ++m) add2(acc[m], b);
         }
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) {
-            if (a.add[m] != nullptr) {
-                const double2 t = ld2(a.add[m] + 2 * i);
-                acc[m].x += t.x;
-                acc[m].y += t.y;
-            }
+            if (a.add[m] != nullptr) add2(acc[m], ld2(a.add[m] + 2 * i));
             st2(a.out[m] + 2 * i, acc[m]);
         }
     }
 }
 
-// res[m] = sum_k W[m][k] in[k] + (u0 - u[m]) + tau[m];  resnorm[m] = max |res[m]|
-template <int NOUT>
-__global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_constant__ CollocArgs a) {
+// The sweep's node combinations in the reference's own order of operations (see sdc_b200.h, sdcb200_colloc_sweep).
+struct SweepArgs {
+    const double* in[SDCB200_MAX_TERMS];  // f[j] (NCOMP = 1) or f[j].impl, f[j].expl interleaved (NCOMP = 2)
+    double* out[SDCB200_MAX_NODES];
+    const double* add[SDCB200_MAX_NODES];
+    const double* u[SDCB200_MAX_NODES];
+    const double* base;
+    double Wq[SDCB200_MAX_NODES * SDCB200_MAX_NODES];  // phase 1: quadrature coefficients dt*Q[m][j]
+    double Wi[SDCB200_MAX_NODES * SDCB200_MAX_NODES];  // phase 2: implicit QDelta coefficients (sign folded in)
+    double We[SDCB200_MAX_NODES * SDCB200_MAX_NODES];  // phase 2: explicit QDelta coefficients (NCOMP = 2 only)
+    double dt2;                                        // phase 2, NCOMP = 2: outer factor dt
+    double* resnorm;
+    long long count2;
+    int nj;     // input nodes
+    int flags;  // SDCB200_SWEEP_*
+};
+
+template <int NCOMP>
+__device__ __forceinline__ double2 node_value(const SweepArgs& a, int j, long long i) {
+    if (NCOMP == 1) return ld2(a.in[j] + 2 * i);
+    double2 v = ld2(a.in[2 * j] + 2 * i);
+    add2(v, ld2(a.in[2 * j + 1] + 2 * i));  // f[j].impl + f[j].expl  (imex_1st_order.py:53)
+    return v;
+}
+
+template <int NOUT, int NCOMP>
+__device__ __forceinline__ void sweep_terms(const SweepArgs& a, long long i, double2 (&acc)[NOUT]) {
+    if (a.flags & SDCB200_SWEEP_QUADRATURE) {
+#pragma unroll 2
+        for (int j = 0; j < a.nj; ++j) {
+            const double2 v = node_value<NCOMP>(a, j, i);
+#pragma unroll
+            for (int m = 0; m < NOUT; ++m) mul_add(acc[m], a.Wq[m * a.nj + j], v);
+        }
+    }
+    if (a.flags & SDCB200_SWEEP_QDELTA) {
+#pragma unroll 2
+        for (int j = 0; j < a.nj; ++j) {  // second read of f[j]: served by L1/L2, no extra DRAM traffic
+            if (NCOMP == 1) {
+                const double2 v = ld2(a.in[j] + 2 * i);
+#pragma unroll
+                for (int m = 0; m < NOUT; ++m) mul_add(acc[m], a.Wi[m * a.nj + j], v);  // (dt*QI[m][j]) * f[j]
+            } else {
+                const double2 vi = ld2(a.in[2 * j] + 2 * i), ve = ld2(a.in[2 * j + 1] + 2 * i);
+#pragma unroll
+                for (int m = 0; m < NOUT; ++m) {  // dt * (QI[m][j]*f[j].impl + QE[m][j]*f[j].expl), imex_1st_order.py:83,95
+                    double2 t;
+                    t.x = __dadd_rn(__dmul_rn(a.Wi[m * a.nj + j], vi.x), __dmul_rn(a.We[m * a.nj + j], ve.x));
+                    t.y = __dadd_rn(__dmul_rn(a.Wi[m * a.nj + j], vi.y), __dmul_rn(a.We[m * a.nj + j], ve.y));
+                    mul_add(acc[m], a.dt2, t);
+                }
+            }
+        }
+    }
+}
+
+template <int NOUT, int NCOMP>
+__global__ void __launch_bounds__(kThreads) colloc_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    const long long stride = (long long)gridDim.x * kThreads;
+    const bool base_first = a.flags & SDCB200_SWEEP_BASE_FIRST;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.count2; i += stride) {
+        double2 acc[NOUT];
+        double2 b = make_double2(0.0, 0.0);
+        if (a.base != nullptr) b = ld2(a.base + 2 * i);
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) acc[m] = base_first ? b : make_double2(0.0, 0.0);
+        sweep_terms<NOUT, NCOMP>(a, i, acc);
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) {
+            if (!base_first && a.base != nullptr) add2(acc[m], b);
+            if (a.add[m] != nullptr) add2(acc[m], ld2(a.add[m] + 2 * i));
+            st2(a.out[m] + 2 * i, acc[m]);
+        }
+    }
+}
+
+// res[m] = sum_j (dt*Q[m][j]) f[j] + (u0 - u[m]) + tau[m];  resnorm[m] = max |res[m]|   (core/sweeper.py:186-195)
+template <int NOUT, int NCOMP>
+__global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_constant__ SweepArgs a) {
     __shared__ double scratch[33];
     double vmax[NOUT];
     unsigned bad = 0;  // bit m: a NaN was seen in res[m] (fmax would silently drop it; numpy's max would not)
@@ -72,27 +150,14 @@ __global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_
         double2 acc[NOUT];
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) acc[m] = make_double2(0.0, 0.0);
-#pragma unroll 4
-        for (int k = 0; k < a.nin; ++k) {
-            const double2 v = ld2(a.in[k] + 2 * i);
-#pragma unroll
-            for (int m = 0; m < NOUT; ++m) {
-                const double w = a.W[m * a.nin + k];
-                acc[m].x = fma(w, v.x, acc[m].x);
-                acc[m].y = fma(w, v.y, acc[m].y);
-            }
-        }
+        sweep_terms<NOUT, NCOMP>(a, i, acc);
         const double2 u0 = ld2(a.base + 2 * i);
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) {
             const double2 um = ld2(a.u[m] + 2 * i);
-            acc[m].x += (u0.x - um.x);  // same association as sweeper.py:188  (res += u[0] - u[m+1])
-            acc[m].y += (u0.y - um.y);
-            if (a.add[m] != nullptr) {
-                const double2 t = ld2(a.add[m] + 2 * i);
-                acc[m].x += t.x;
-                acc[m].y += t.y;
-            }
+            acc[m].x = __dadd_rn(acc[m].x, __dadd_rn(u0.x, -um.x));  // res += u[0] - u[m+1]  (sweeper.py:188)
+            acc[m].y = __dadd_rn(acc[m].y, __dadd_rn(u0.y, -um.y));
+            if (a.add[m] != nullptr) add2(acc[m], ld2(a.add[m] + 2 * i));
             if (a.out[m] != nullptr) st2(a.out[m] + 2 * i, acc[m]);
             vmax[m] = fmax(vmax[m], fmax(fabs(acc[m].x), fabs(acc[m].y)));
             if (acc[m].x != acc[m].x || acc[m].y != acc[m].y) bad |= 1u << m;
@@ -130,8 +195,8 @@ __global__ void __launch_bounds__(kThreads) axpby_kernel(long long count2, doubl
         v.y *= a;
         if (y != nullptr) {
             const double2 w = ld2(y + 2 * i);
-            v.x = fma(b, w.x, v.x);
-            v.y = fma(b, w.y, v.y);
+            v.x = __dadd_rn(v.x, __dmul_rn(b, w.x));  // numpy rounds a*x, b*y and the sum separately
+            v.y = __dadd_rn(v.y, __dmul_rn(b, w.y));
         }
         st2(out + 2 * i, v);
     }
@@ -239,37 +304,87 @@ int sdcb200_colloc_apply(long long count, int nout, int nin, const double* W_hos
     return 0;
 }
 
-int sdcb200_colloc_residual(long long count, int M, int nin, const double* W_host, const double* const* in,
-                            const double* u0, const double* const* u, const double* const* tau,
-                            double* const* res_out, double* resnorm_dev, void* stream) {
-    SDC_REQUIRE(M >= 1 && M <= SDCB200_MAX_NODES, "M out of range");
-    SDC_REQUIRE(nin >= 0 && nin <= SDCB200_MAX_TERMS, "nin out of range");
+namespace {
+int fill_sweep_args(SweepArgs& a, long long count, int nout, int nj, int ncomp, int flags, const double* Wq,
+                    const double* Wi, const double* We, double dt2, const double* const* in, const double* base,
+                    const double* const* add) {
+    SDC_REQUIRE(nout >= 1 && nout <= SDCB200_MAX_NODES, "number of output nodes out of range");
+    SDC_REQUIRE(nj >= 0 && nj <= SDCB200_MAX_NODES, "number of input nodes out of range");
+    SDC_REQUIRE(ncomp == 1 || ncomp == 2, "ncomp must be 1 (mesh) or 2 (imex_mesh)");
     SDC_REQUIRE(count >= 0 && count % 2 == 0, "count must be even");
-    SDC_REQUIRE(u0 != nullptr && aligned16(u0), "u0 missing or misaligned");
-    CollocArgs a;
+    SDC_REQUIRE(!(flags & SDCB200_SWEEP_QUADRATURE) || Wq != nullptr, "quadrature coefficients missing");
+    SDC_REQUIRE(!(flags & SDCB200_SWEEP_QDELTA) || (Wi != nullptr && (ncomp == 1 || We != nullptr)),
+                "QDelta coefficients missing");
     memset(&a, 0, sizeof(a));
-    for (int k = 0; k < nin; ++k) {
+    for (int k = 0; k < nj * ncomp; ++k) {
         SDC_REQUIRE(in[k] != nullptr && aligned16(in[k]), "input field missing or misaligned");
         a.in[k] = in[k];
     }
+    for (int m = 0; m < nout; ++m) {
+        a.add[m] = add ? add[m] : nullptr;
+        SDC_REQUIRE(aligned16(a.add[m]), "tau field misaligned");
+        for (int j = 0; j < nj; ++j) {
+            a.Wq[m * nj + j] = (flags & SDCB200_SWEEP_QUADRATURE) ? Wq[m * nj + j] : 0.0;
+            a.Wi[m * nj + j] = (flags & SDCB200_SWEEP_QDELTA) ? Wi[m * nj + j] : 0.0;
+            a.We[m * nj + j] = ((flags & SDCB200_SWEEP_QDELTA) && ncomp == 2) ? We[m * nj + j] : 0.0;
+        }
+    }
+    SDC_REQUIRE(aligned16(base), "base field misaligned");
+    a.base = base;
+    a.dt2 = dt2;
+    a.nj = nj;
+    a.flags = flags;
+    a.count2 = count / 2;
+    return 0;
+}
+}  // namespace
+
+int sdcb200_colloc_sweep(long long count, int nout, int nj, int ncomp, int flags, const double* Wq_host,
+                         const double* Wi_host, const double* We_host, double dt2, const double* const* in,
+                         const double* base, const double* const* add, double* const* out, void* stream) {
+    SweepArgs a;
+    if (int rc = fill_sweep_args(a, count, nout, nj, ncomp, flags, Wq_host, Wi_host, We_host, dt2, in, base, add)) return rc;
+    SDC_REQUIRE(!(flags & SDCB200_SWEEP_BASE_FIRST) || base != nullptr, "BASE_FIRST needs a base field");
+    for (int m = 0; m < nout; ++m) {
+        SDC_REQUIRE(out[m] != nullptr && aligned16(out[m]), "output field missing or misaligned");
+        a.out[m] = out[m];
+    }
+    if (count == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int grid = stream_grid(a.count2);
+    switch (nout * 2 + (ncomp - 1)) {
+#define CASE(N) \
+    case 2 * N: colloc_sweep_kernel<N, 1><<<grid, kThreads, 0, s>>>(a); break; \
+    case 2 * N + 1: colloc_sweep_kernel<N, 2><<<grid, kThreads, 0, s>>>(a); break;
+        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
+#undef CASE
+    }
+    SDC_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sdcb200_colloc_residual(long long count, int M, int nj, int ncomp, const double* Wq_host, const double* const* in,
+                            const double* u0, const double* const* u, const double* const* tau,
+                            double* const* res_out, double* resnorm_dev, void* stream) {
+    SDC_REQUIRE(u0 != nullptr && aligned16(u0), "u0 missing or misaligned");
+    SweepArgs a;
+    if (int rc = fill_sweep_args(a, count, M, nj, ncomp, SDCB200_SWEEP_QUADRATURE, Wq_host, nullptr, nullptr, 0.0, in, u0,
+                                 tau)) return rc;
     for (int m = 0; m < M; ++m) {
         SDC_REQUIRE(u[m] != nullptr && aligned16(u[m]), "node value missing or misaligned");
         a.u[m] = u[m];
-        a.add[m] = tau ? tau[m] : nullptr;
         a.out[m] = res_out ? res_out[m] : nullptr;
-        SDC_REQUIRE(aligned16(a.add[m]) && aligned16(a.out[m]), "tau / residual field misaligned");
-        for (int k = 0; k < nin; ++k) a.W[m * nin + k] = W_host[m * nin + k];
+        SDC_REQUIRE(aligned16(a.out[m]), "residual field misaligned");
     }
-    a.base = u0;
-    a.nin = nin;
-    a.count2 = count / 2;
     a.resnorm = resnorm_dev;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SDC_CUDA_OK(cudaMemsetAsync(resnorm_dev, 0, sizeof(double) * M, s));
     if (count == 0) return 0;
     const int grid = stream_grid(a.count2);
-    switch (M) {
-#define CASE(N) case N: colloc_residual_kernel<N><<<grid, kThreads, 0, s>>>(a); break;
+    switch (M * 2 + (ncomp - 1)) {
+#define CASE(N) \
+    case 2 * N: colloc_residual_kernel<N, 1><<<grid, kThreads, 0, s>>>(a); break; \
+    case 2 * N + 1: colloc_residual_kernel<N, 2><<<grid, kThreads, 0, s>>>(a); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }

@@ -186,8 +186,15 @@ class mesh:
     def _same(self, other):
         return isinstance(other, mesh) and other._lay == self._lay and other._ncomp == self._ncomp
 
+    def _touch(self):
+        """Count a write that went through a kernel or the transport (torch's own version counter only sees torch
+        operations); the sweepers use both counters to know whether a cached residual is still valid."""
+        self._kver = getattr(self, "_kver", 0) + 1
+
     def _lin(self, a, b, other, out=None):
         """out = a*self + b*other through the axpby kernel (walls stay zero)."""
+        if out is not None:
+            out._touch()
         out = self._new_like() if out is None else out
         get_backend().axpby(a, self.vol, b, None if other is None else other.vol, out.vol)
         return out
@@ -285,9 +292,11 @@ class mesh:
         return comm.Issend(self, dest=dest, tag=tag)
 
     def irecv(self, source=None, tag=None, comm=None):
+        self._touch()
         return comm.Irecv(self, source=source, tag=tag)
 
     def bcast(self, root=None, comm=None):
+        self._touch()
         comm.Bcast(self, root=root)
         return self
 

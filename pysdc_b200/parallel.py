@@ -145,6 +145,17 @@ class TorchComm:
             out = t.tolist()
         return out if is_list else out[0]
 
+    def allreduce_device(self, t, op=MAX):
+        """In-place all-reduce of a small device vector (residual norms): NCCL reduces it where it lives; a host-staged
+        transport (gloo) takes the round trip through the host."""
+        if self._host_staged and t.is_cuda:
+            h = t.cpu()
+            dist.all_reduce(h, op=_OPS[op], group=self.group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=_OPS[op], group=self.group)
+        return t
+
     def allgather(self, obj):
         out = [None] * self.size
         dist.all_gather_object(out, obj, group=self.group)

@@ -19,8 +19,16 @@ What changes is how the work is done:
   device->host read of a sweep happens here, because ``L.status.residual`` has to be a Python float for
   ``CheckConvergence`` (convergence_controller_classes/check_convergence.py:75-76).
 
-Solutions and right-hand sides are updated in place in the buffers ``L.u[m]`` / ``L.f[m]`` already own.
+Rounding: the node combinations go through ``sdcb200_colloc_sweep``, which performs the reference's floating-point
+operations in the reference's order (scalar coefficient first, every product and sum rounded on its own, quadrature
+terms before QDelta terms before ``u[0]`` before ``tau``), so given identical solves a sweep reproduces numpy bit for bit.
+
+Solutions and right-hand sides are updated in place in the buffers ``L.u[m]`` / ``L.f[m]`` already own — unless somebody
+else holds a reference to such a field (the reference REBINDS ``L.u[m+1]`` to a fresh object in every sweep, so code like
+``uold[1:] = L.u[1:]`` in controller_MPI.py:475 keeps the old values): then the sweep switches to a fresh buffer first.
 """
+import sys
+
 import numpy as np
 import torch
 
@@ -56,6 +64,10 @@ class _SweepCommon:
 
     imex = False
 
+    @property
+    def _ncomp(self):
+        return 2 if self.imex else 1
+
     # ---- helpers ----------------------------------------------------------------------------------------------------
     def _f_inputs(self, L, first=1):
         """Flat device views of f[first..M], node-major then component (impl, expl)."""
@@ -68,15 +80,26 @@ class _SweepCommon:
                 ins.append(f.flat)
         return ins
 
-    def _expand(self, WI, WE=None):
-        """(rows x M) coefficient blocks -> (rows x M*C) matching ``_f_inputs`` ordering."""
-        if not self.imex:
-            return np.ascontiguousarray(WI)
-        WE = WI if WE is None else WE
-        out = np.empty((WI.shape[0], 2 * WI.shape[1]))
-        out[:, 0::2] = WI
-        out[:, 1::2] = WE
-        return out
+    @staticmethod
+    def _own(lst, i):
+        """``lst[i]`` ready to be overwritten in place: if anything besides the level's list refers to the object (an
+        ``uold`` list, a hook's record, a user variable) it is replaced by a fresh copy first, which leaves the other
+        holder with the old values exactly as the reference's rebinding does."""
+        x = lst[i]
+        if sys.getrefcount(x) > 3:  # the list, the local name, getrefcount's argument
+            lst[i] = type(x)(x)
+        del x
+        return lst[i]
+
+    @staticmethod
+    def _field_key(x):
+        return None if x is None else (id(x), x._buf._version, getattr(x, "_kver", 0))
+
+    def _residual_key(self, L):
+        """Identity + version of everything compute_residual reads (core/sweeper.py:164-215)."""
+        return (L.dt, L.params.residual_type, tuple(self._field_key(u) for u in L.u),
+                tuple(self._field_key(f) for f in L.f[1:]), tuple(self._field_key(t) for t in L.tau),
+                self.coll.Qmat.tobytes())
 
     def _scratch(self, L, count):
         """M reusable right-hand-side fields per level (never visible to the caller)."""
@@ -119,6 +142,7 @@ class _SweepCommon:
             raise ParameterError(f"initial_guess option {guess} not implemented")
         L.status.unlocked = True
         L.status.updated = True
+        self._res_cache = None
 
     # ---- integrate (generic_implicit.py:29-49, imex_1st_order.py:37-55) ---------------------------------------------
     def integrate(self):
@@ -126,8 +150,7 @@ class _SweepCommon:
         P = L.prob
         M = self.coll.num_nodes
         me = [P.dtype_u(P.init) for _ in range(M)]
-        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
-        get_backend().colloc_apply(W, self._f_inputs(L), None, None, [x.flat for x in me])
+        get_backend().colloc_sweep(self._f_inputs(L), self._ncomp, [x.flat for x in me], Wq=L.dt * self.coll.Qmat[1:, 1:])
         return me
 
     # ---- one sweep (generic_implicit.py:51-103, imex_1st_order.py:57-108) -------------------------------------------
@@ -145,11 +168,19 @@ class _SweepCommon:
         batched = hasattr(P, "solve_system_batch") and hasattr(P, "eval_f_batch")
 
         # known terms of every node: u0 + dt*(Q - QDelta) F(u^k) + tau, one fused pass
+        # (integrate(), then `integral[m] -= dt*QDelta[m+1, j] f[j]` for all j, `+= u[0]`, `+= tau[m]`: generic_implicit.py:
+        # 70-82, imex_1st_order.py:77-88, in that order of operations)
         rhs = self._scratch(L, M)
-        W = self._expand(dt * (Q[1:, 1:] - QI[1:, 1:]), None if QE is None else dt * (Q[1:, 1:] - QE[1:, 1:]))
         taus = [None if t is None else t.flat for t in L.tau]
-        be.colloc_apply(W, self._f_inputs(L), L.u[0].flat, taus if any(t is not None for t in taus) else None,
-                        [r.flat for r in rhs])
+        if self.imex:
+            qd = dict(Wi=-QI[1:, 1:], We=-QE[1:, 1:], dt2=dt)
+        else:
+            qd = dict(Wi=-(dt * QI[1:, 1:]))
+        be.colloc_sweep(self._f_inputs(L), self._ncomp, [r.flat for r in rhs], Wq=dt * Q[1:, 1:], base=L.u[0].flat,
+                        adds=taus if any(t is not None for t in taus) else None, **qd)
+        for m in range(1, M + 1):
+            self._own(L.u, m)
+            self._own(L.f, m)
 
         strictly_lower_empty = not np.any(np.tril(QI[1:, 1:], k=-1)) and (QE is None or not np.any(np.tril(QE[1:, 1:], k=-1)))
         if batched and strictly_lower_empty and (self.imex or all(a != 0 for a in alphas)):
@@ -161,10 +192,14 @@ class _SweepCommon:
             for m in range(M):
                 if m > 0:
                     # add dt*QDelta[m+1, j] f(u_j^{k+1}) for the nodes j <= m already updated in this sweep
-                    Wn = self._expand(dt * QI[m + 1: m + 2, 1: m + 1], None if QE is None else dt * QE[m + 1: m + 2, 1: m + 1])
-                    if np.any(Wn):
-                        ins = self._f_inputs(L)[: Wn.shape[1]]
-                        be.colloc_apply(Wn, ins, rhs[m].flat, None, [rhs[m].flat])
+                    # (generic_implicit.py:87-89, imex_1st_order.py:92-95), in place on rhs[m]
+                    ins = self._f_inputs(L)[: m * self._ncomp]
+                    if self.imex:
+                        qd = dict(Wi=QI[m + 1: m + 2, 1: m + 1], We=QE[m + 1: m + 2, 1: m + 1], dt2=dt)
+                    else:
+                        qd = dict(Wi=dt * QI[m + 1: m + 2, 1: m + 1])
+                    if np.any(qd["Wi"]) or (self.imex and np.any(qd["We"])):
+                        be.colloc_sweep(ins, self._ncomp, [rhs[m].flat], base=rhs[m].flat, base_first=True, **qd)
                 if alphas[m] == 0 and not self.imex:
                     L.u[m + 1][:] = rhs[m]  # generic_implicit.py:93-94
                 elif batched:
@@ -176,6 +211,7 @@ class _SweepCommon:
                 else:
                     L.f[m + 1] = P.eval_f(L.u[m + 1], times[m])
         L.status.updated = True
+        self._res_cache = None
         return None
 
     # ---- residual (core/sweeper.py:164-215) -------------------------------------------------------------------------
@@ -184,9 +220,18 @@ class _SweepCommon:
         if stage in self.params.skip_residual_computation:
             L.status.residual = 0.0 if L.status.residual is None else L.status.residual
             return None
+        # the reference's controllers ask for the residual twice per iteration with nothing changed in between
+        # (controller_nonMPI.py:493 after :573): the second request is answered from the first when neither a sweep
+        # (L.status.updated) nor anybody else touched the fields the residual reads
+        key = self._residual_key(L)
+        cache = getattr(self, "_res_cache", None)
+        if (not L.status.updated and cache is not None and cache[0] == key
+                and not getattr(self.params, "store_residual", False)):
+            L.status.residual = cache[1]
+            return None
         be = get_backend()
         M = self.coll.num_nodes
-        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
+        Wq = L.dt * self.coll.Qmat[1:, 1:]
         taus = [None if t is None else t.flat for t in L.tau]
         res_out = None
         if getattr(self.params, "store_residual", False):
@@ -197,15 +242,20 @@ class _SweepCommon:
         if "_resnorm" not in self.__dict__:
             self._resnorm = be.zeros(9)
         norms_dev = self._resnorm
-        be.colloc_residual(W, self._f_inputs(L), L.u[0].flat, [u.flat for u in L.u[1:]],
+        be.colloc_residual(Wq, self._f_inputs(L), self._ncomp, L.u[0].flat, [u.flat for u in L.u[1:]],
                            taus if any(t is not None for t in taus) else None, res_out, norms_dev[:M])
         rtype = L.params.residual_type
         if rtype.endswith("_rel"):
             be.maxabs_async(L.u[0].vol, norms_dev[8:9])
+        comm = L.u[0].comm
+        distributed = comm is not None and getattr(comm, "size", 1) > 1
+        if distributed and hasattr(comm, "allreduce_device"):
+            from .comm import MAX
+            comm.allreduce_device(norms_dev, MAX)  # one MAX all-reduce on the device vector, then the single read
+            distributed = False
         host = norms_dev.cpu().tolist()  # the one device->host read of a sweep
         res_norm, u0_norm = host[:M], host[8]
-        comm = L.u[0].comm
-        if comm is not None and getattr(comm, "size", 1) > 1:
+        if distributed:
             from .comm import MAX
             res_norm = comm.allreduce(res_norm, op=MAX)
             u0_norm = comm.allreduce(u0_norm, op=MAX)
@@ -221,6 +271,7 @@ class _SweepCommon:
             raise ParameterError(f"residual_type = {rtype} not implemented, choose full_abs, last_abs, full_rel or "
                                  "last_rel instead")
         L.status.updated = False
+        self._res_cache = (key, L.status.residual)
         return None
 
     def _residual_fields(self):
@@ -228,11 +279,11 @@ class _SweepCommon:
         L = self.level
         be = get_backend()
         M = self.coll.num_nodes
-        W = self._expand(L.dt * self.coll.Qmat[1:, 1:])
         taus = [None if t is None else t.flat for t in L.tau]
         out = [L.prob.dtype_u(L.prob.init) for _ in range(M)]
-        be.colloc_residual(W, self._f_inputs(L), L.u[0].flat, [u.flat for u in L.u[1:]],
-                           taus if any(t is not None for t in taus) else None, [r.flat for r in out], be.zeros(M))
+        be.colloc_residual(L.dt * self.coll.Qmat[1:, 1:], self._f_inputs(L), self._ncomp, L.u[0].flat,
+                           [u.flat for u in L.u[1:]], taus if any(t is not None for t in taus) else None,
+                           [r.flat for r in out], be.zeros(M))
         return out
 
     # ---- end point (generic_implicit.py:105-131, imex_1st_order.py:110-137) -----------------------------------------
@@ -242,10 +293,11 @@ class _SweepCommon:
         if self.coll.right_is_node and not self.params.do_coll_update:
             L.uend = P.dtype_u(L.u[-1])
         else:
+            # uend = u[0]; uend += dt*w_m f[m+1] for all m; uend += tau[-1]   (generic_implicit.py:123-129)
             L.uend = P.dtype_u(P.init)
-            W = self._expand((L.dt * self.coll.weights)[None, :])
             tau = None if L.tau[-1] is None else [L.tau[-1].flat]
-            get_backend().colloc_apply(W, self._f_inputs(L), L.u[0].flat, tau, [L.uend.flat])
+            get_backend().colloc_sweep(self._f_inputs(L), self._ncomp, [L.uend.flat],
+                                       Wq=(L.dt * self.coll.weights)[None, :], base=L.u[0].flat, adds=tau, base_first=True)
         return None
 
 

@@ -83,14 +83,45 @@ class NumpyBackend:
                 acc += _np(adds[m])
             _np(o)[:] = acc
 
-    def colloc_residual(self, W, ins, u0, us, taus, res_outs, resnorm):
+    @staticmethod
+    def _node_values(ins, ncomp):
+        vals = [_np(t).copy() for t in ins]
+        return vals if ncomp == 1 else [vals[2 * j] + vals[2 * j + 1] for j in range(len(vals) // 2)]
+
+    def colloc_sweep(self, ins, ncomp, outs, Wq=None, Wi=None, We=None, dt2=0.0, base=None, adds=None,
+                     base_first=False):
+        """Same order of operations as sdcb200_colloc_sweep (include/sdc_b200.h)."""
         self.launches += 1
-        W = np.asarray(W, dtype=float).reshape(len(us), len(ins))
-        vals = [_np(t) for t in ins]
+        nj = len(ins) // ncomp
+        raw = [_np(t).copy() for t in ins]
+        F = self._node_values(ins, ncomp)
+        b = None if base is None else _np(base).copy()
+        shape = lambda W: np.asarray(W, dtype=float).reshape(len(outs), nj)  # noqa: E731
+        for m, o in enumerate(outs):
+            acc = b.copy() if base_first else np.zeros(o.numel())
+            if Wq is not None:
+                for j in range(nj):
+                    acc += shape(Wq)[m, j] * F[j]
+            if Wi is not None:
+                for j in range(nj):
+                    if ncomp == 1:
+                        acc += shape(Wi)[m, j] * raw[j]
+                    else:
+                        acc += dt2 * (shape(Wi)[m, j] * raw[2 * j] + shape(We)[m, j] * raw[2 * j + 1])
+            if b is not None and not base_first:
+                acc += b
+            if adds is not None and adds[m] is not None:
+                acc += _np(adds[m])
+            _np(o)[:] = acc
+
+    def colloc_residual(self, Wq, ins, ncomp, u0, us, taus, res_outs, resnorm):
+        self.launches += 1
+        F = self._node_values(ins, ncomp)
+        Wq = np.asarray(Wq, dtype=float).reshape(len(us), len(F))
         for m, u in enumerate(us):
             acc = np.zeros(u.numel())
-            for k, v in enumerate(vals):
-                acc += W[m, k] * v
+            for j, v in enumerate(F):
+                acc += Wq[m, j] * v
             acc += _np(u0) - _np(u)
             if taus is not None and taus[m] is not None:
                 acc += _np(taus[m])

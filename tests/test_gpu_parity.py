@@ -69,7 +69,8 @@ def test_streaming_kernels(cuda_backend, count):
     assert be.maxabs(tx) == float(np.max(np.abs(x)))
     x[count // 2] = np.nan
     assert np.isnan(be.maxabs(torch.from_numpy(x).cuda()))
-    # collocation: 3 outputs from 5 inputs, base and one optional add
+    # generic linear combination: 3 outputs from 5 inputs, base and one optional add; bit-exact against numpy evaluated
+    # in the same order (products and sums rounded separately: no FMA contraction in the kernels)
     ins = [rng.standard_normal(count) for _ in range(5)]
     W = rng.standard_normal((3, 5))
     base, add1 = rng.standard_normal(count), rng.standard_normal(count)
@@ -77,17 +78,94 @@ def test_streaming_kernels(cuda_backend, count):
     be.colloc_apply(W, [torch.from_numpy(v).cuda() for v in ins], torch.from_numpy(base).cuda(),
                     [None, torch.from_numpy(add1).cuda(), None], outs)
     for m in range(3):
-        want = sum(W[m, k] * ins[k] for k in range(5)) + base + (add1 if m == 1 else 0.0)
-        np.testing.assert_allclose(outs[m].cpu().numpy(), want, rtol=0, atol=1e-14)
-    us = [rng.standard_normal(count) for _ in range(3)]
-    norms = torch.zeros(3, dtype=torch.float64, device="cuda")
-    res = [torch.empty(count, dtype=torch.float64, device="cuda") for _ in range(3)]
-    be.colloc_residual(W, [torch.from_numpy(v).cuda() for v in ins], torch.from_numpy(base).cuda(),
-                       [torch.from_numpy(v).cuda() for v in us], None, res, norms)
-    for m in range(3):
-        want = sum(W[m, k] * ins[k] for k in range(5)) + (base - us[m])
-        np.testing.assert_allclose(res[m].cpu().numpy(), want, rtol=0, atol=1e-14)
-        assert abs(float(norms[m]) - np.max(np.abs(want))) < 1e-14
+        want = np.zeros(count)
+        for k in range(5):
+            want += W[m, k] * ins[k]
+        want += base
+        if m == 1:
+            want += add1
+        assert np.array_equal(outs[m].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("count", [2, 510, 1 << 18])
+@pytest.mark.parametrize("imex", [False, True])
+def test_sweep_combinations_reproduce_numpy_bit_for_bit(cuda_backend, count, imex):
+    """sdcb200_colloc_sweep / sdcb200_colloc_residual against the reference's own loops written out in numpy
+    (generic_implicit.py:29-49,70-89,123-129; imex_1st_order.py:37-55,77-95,128-135; core/sweeper.py:186-195):
+    identical bits, not just close."""
+    import torch
+
+    be = cuda_backend
+    rng = np.random.default_rng(count + imex)
+    M, dt = 4, 0.37
+    Q, QI, QE = rng.standard_normal((M, M)), np.tril(rng.standard_normal((M, M))), np.tril(rng.standard_normal((M, M)), -1)
+    nc = 2 if imex else 1
+    f = [[rng.standard_normal(count) for _ in range(nc)] for _ in range(M)]  # f[j] (or f[j].impl, f[j].expl)
+    u0, tau = rng.standard_normal(count), [rng.standard_normal(count) for _ in range(M)]
+    us = [rng.standard_normal(count) for _ in range(M)]
+    dev = lambda v: torch.from_numpy(v).cuda()  # noqa: E731
+    ins = [dev(c) for fj in f for c in fj]
+    F = [fj[0] + fj[1] if imex else fj[0] for fj in f]
+
+    def integrate():
+        me = []
+        for m in range(M):
+            me.append(np.zeros(count))
+            for j in range(M):
+                me[-1] += dt * Q[m, j] * F[j]
+        return me
+
+    # integrate
+    outs = [torch.empty(count, dtype=torch.float64, device="cuda") for _ in range(M)]
+    be.colloc_sweep(ins, nc, outs, Wq=dt * Q)
+    for m, want in enumerate(integrate()):
+        assert np.array_equal(outs[m].cpu().numpy(), want)
+    # known terms of update_nodes
+    integral = integrate()
+    for m in range(M):
+        for j in range(M):
+            if imex:
+                integral[m] -= dt * (QI[m, j] * f[j][0] + QE[m, j] * f[j][1])
+            else:
+                integral[m] -= dt * QI[m, j] * f[j][0]
+        integral[m] += u0
+        if m != 2:
+            integral[m] += tau[m]
+    qd = dict(Wi=-QI, We=-QE, dt2=dt) if imex else dict(Wi=-(dt * QI))
+    be.colloc_sweep(ins, nc, outs, Wq=dt * Q, base=dev(u0), adds=[None if m == 2 else dev(tau[m]) for m in range(M)], **qd)
+    for m in range(M):
+        assert np.array_equal(outs[m].cpu().numpy(), integral[m]), m
+    # new-node additions, in place on rhs
+    m = 3
+    rhs = integral[m].copy()
+    for j in range(m):
+        if imex:
+            rhs += dt * (QI[m, j] * f[j][0] + QE[m, j] * f[j][1])
+        else:
+            rhs += dt * QI[m, j] * f[j][0]
+    buf = dev(integral[m])
+    qd = dict(Wi=QI[m: m + 1, :m], We=QE[m: m + 1, :m], dt2=dt) if imex else dict(Wi=dt * QI[m: m + 1, :m])
+    be.colloc_sweep(ins[: m * nc], nc, [buf], base=buf, base_first=True, **qd)
+    assert np.array_equal(buf.cpu().numpy(), rhs)
+    # end point
+    w = rng.standard_normal(M)
+    uend = u0.copy()
+    for j in range(M):
+        uend += dt * w[j] * F[j]
+    uend += tau[-1]
+    out = torch.empty(count, dtype=torch.float64, device="cuda")
+    be.colloc_sweep(ins, nc, [out], Wq=(dt * w)[None, :], base=dev(u0), adds=[dev(tau[-1])], base_first=True)
+    assert np.array_equal(out.cpu().numpy(), uend)
+    # residual
+    res = integrate()
+    norms = torch.zeros(M, dtype=torch.float64, device="cuda")
+    res_out = [torch.empty(count, dtype=torch.float64, device="cuda") for _ in range(M)]
+    be.colloc_residual(dt * Q, ins, nc, dev(u0), [dev(u) for u in us], [dev(t) for t in tau], res_out, norms)
+    for m in range(M):
+        res[m] += u0 - us[m]
+        res[m] += tau[m]
+        assert np.array_equal(res_out[m].cpu().numpy(), res[m])
+        assert float(norms[m]) == np.max(np.abs(res[m]))
 
 
 @pytest.mark.parametrize("ndim,n,bc", [(1, 5, "dirichlet-zero"), (1, 1023, "dirichlet-zero"), (1, 6, "periodic"),

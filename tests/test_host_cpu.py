@@ -34,7 +34,9 @@ def test_sweep_dump(name):
     pc.check_sweep_dump(name)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("run_") if "255" not in n and "63_K4" not in n])
+# the BASELINE-size fixtures (run_config*: minutes of CPU each) are checked on the GPU only
+@pytest.mark.parametrize("name", [n for n in golden_names("run_")
+                                  if "255" not in n and "63_K4" not in n and not n.startswith("run_config")])
 def test_run(name):
     # 1-D grids are badly conditioned (kappa ~ 1e4): CG loses orthogonality and its iteration count depends on
     # rounding details at the 10 % level; SDC iteration counts and the solution are unaffected
@@ -59,3 +61,82 @@ def test_polynomial_preconditioner_host_semantics():
         heatNd_unforced(nvars=(32, 32), nu=0.1, freq=(2, 2), bc="periodic", solver_type="CG", preconditioner="chebyshev")
     with pytest.raises(ProblemError):
         heatNd_unforced(**dict(kw, preconditioner="jacobi"))
+
+
+def _small_level(qi="LU"):
+    from pysdc_b200.core import Step
+
+    spec = dict(problem="heatNd_unforced", sweeper="generic_implicit",
+                problem_params=dict(nvars=[15, 15], nu=0.1, freq=[2, 2], bc="dirichlet-zero", solver_type="CG",
+                                    lintol=1e-12, liniter=1000),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI=qi), level_params=dict(dt=0.01),
+                step_params=dict(maxiter=5))
+    S = Step(pc.make_description(spec))
+    L = S.levels[0]
+    L.status.time = 0.0
+    S.init_step(L.prob.u_exact(0.0))
+    L.sweep.predict()
+    return L
+
+
+@pytest.mark.parametrize("qi", ["LU", "MIN-SR-NS"])
+def test_update_nodes_leaves_held_references_untouched(qi):
+    """The reference rebinds L.u[m+1] / L.f[m+1] to fresh objects in every sweep (generic_implicit.py:96-98), so a
+    caller's ``uold[1:] = L.u[1:]`` (controller_MPI.py:475, hotrod) keeps the old values.  The device sweepers update in
+    place only while nobody else holds the field; otherwise they switch to a fresh buffer first."""
+    L = _small_level(qi)
+    L.sweep.update_nodes()
+    uold, fold = list(L.u), list(L.f)
+    before_u = [u.get().copy() for u in uold]
+    before_f = [f.get().copy() for f in fold]
+    ids = [id(u) for u in L.u]
+    L.sweep.update_nodes()
+    for m in range(1, 4):
+        assert L.u[m] is not uold[m] and L.f[m] is not fold[m]
+        assert np.array_equal(uold[m].get(), before_u[m]) and np.array_equal(fold[m].get(), before_f[m])
+        assert not np.array_equal(L.u[m].get(), before_u[m])
+    del uold, fold
+    # nobody else holds the fields any more: the next sweep works in place again
+    ids = [id(u) for u in L.u]
+    L.sweep.update_nodes()
+    assert [id(u) for u in L.u] == ids
+
+
+def test_second_residual_request_is_answered_from_the_first():
+    """the controllers ask for the residual twice per iteration (controller_nonMPI.py:573 then :493); the
+    second request launches nothing unless a sweep or anybody else touched what the residual reads."""
+    from pysdc_b200 import backend
+
+    be = backend.get_backend()
+    L = _small_level()
+    L.sweep.update_nodes()
+    L.sweep.compute_residual(stage="IT_FINE")
+    first, n0 = L.status.residual, be.launches
+    L.sweep.compute_residual(stage="IT_CHECK")
+    assert be.launches == n0 and L.status.residual == first and not L.status.updated
+    # a received initial value (controller recv: new u[0] object) invalidates it ...
+    L.u[0] = L.prob.dtype_u(L.u[0])
+    L.u[0][:] = 0.5 * L.u[0].get()
+    L.sweep.compute_residual(stage="IT_CHECK")
+    assert be.launches > n0 and L.status.residual != first
+    # ... and so do an in-place write into a field, a new step size, a forcing term, another residual type
+    second = L.status.residual
+    for change in ("inplace", "iadd", "dt", "tau", "rtype"):
+        n0 = be.launches
+        if change == "inplace":
+            L.u[2][:] = 1.01 * L.u[2].get()
+        elif change == "iadd":
+            L.u[3] += L.u[1]
+        elif change == "dt":
+            L.params.dt = 0.02
+        elif change == "tau":
+            L.tau[0] = L.prob.dtype_u(L.u[1])
+        else:
+            L.params.residual_type = "last_abs"
+        L.sweep.compute_residual()
+        assert be.launches > n0, change
+        assert L.status.residual != second or change == "tau", change  # (the max may sit on another node)
+        second = L.status.residual
+    n0 = be.launches
+    L.sweep.compute_residual()
+    assert be.launches == n0

@@ -1,5 +1,7 @@
 """The reference's OWN time-parallel controller (controller_MPI, unmodified) on the torch.distributed-backed mpi4py
-facade, driving the plug-in classes: build container only (needs /root/reference), gloo + numpy test double."""
+facade, driving the plug-in classes.  ``numpy`` variant: gloo + the numpy test double (CPU suite); ``cuda`` variant
+(``-m gpu``): the real CUDA kernels, one process per time slice (NCCL when the box has a GPU per slice, else the slices
+share the device and hand over through gloo).  The reference comes from /root/reference or the shipped oracle/_ref."""
 import json
 import os
 import sys
@@ -9,28 +11,38 @@ import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import ROOT, free_port, load_golden
+from conftest import ROOT, free_port, load_golden, reference_paths
 
-REF = os.environ.get("PYSDC_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pySDC")), reason="reference tree not present")
+REF_PATHS = reference_paths()
+pytestmark = pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
 
 
-def _worker(rank, world, port, name, out_dir):
+def _worker(rank, world, port, name, out_dir, kind, ref_paths):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "qmat_shim"))
-    sys.path.insert(0, REF)
+    for p in reversed(ref_paths):
+        sys.path.insert(0, p)
     import pysdc_b200.mpi_facade
 
     sys.path.insert(0, pysdc_b200.mpi_facade.PATH)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    transport = "gloo"
+    if kind == "cuda":
+        import torch
+
+        transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(transport, rank=rank, world_size=world)
     try:
         from mpi4py import MPI  # the facade
-        from fake_backend import NumpyBackend
         from pysdc_b200 import backend
 
-        backend.set_backend(NumpyBackend())
+        if kind == "cuda":
+            backend.set_backend(backend.CudaBackend())
+        else:
+            from fake_backend import NumpyBackend
+
+            backend.set_backend(NumpyBackend())
         from pySDC.helpers.stats_helper import get_sorted
         from pySDC.implementations.controller_classes.controller_MPI import controller_MPI
 
@@ -56,10 +68,11 @@ def _worker(rank, world, port, name, out_dir):
         dist.destroy_process_group()
 
 
-def test_reference_controller_MPI_on_the_facade(tmp_path):
+@pytest.mark.parametrize("kind", ["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_reference_controller_MPI_on_the_facade(tmp_path, kind):
     name, world = "pfasst_heat2d_imex_63_p4", 4
     _, g = load_golden(name)
-    mp.spawn(_worker, args=(world, free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, free_port(), name, str(tmp_path), kind, REF_PATHS), nprocs=world, join=True)
     niter = []
     for r in range(world):
         niter += [tuple(x) for x in json.load(open(os.path.join(tmp_path, f"niter_{r}.json")))]

@@ -60,7 +60,9 @@ def test_sweep_dumps(oracle, name):
         assert c.niter == int(g["work_" + key]), key
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names("run_") if "63_K4" not in n and "255" not in n])
+# of the BASELINE-size fixtures (run_config*) the oracle replays the two it finishes in seconds
+@pytest.mark.parametrize("name", [n for n in golden_names("run_") if "63_K4" not in n and "255" not in n
+                                  and (not n.startswith("run_config") or n.endswith(("_511", "_256")))])
 def test_full_runs(oracle, name):
     spec, g = load_golden(name)
     out = oracle.run_sdc(spec)
@@ -69,8 +71,13 @@ def test_full_runs(oracle, name):
         assert out["work"][key] == g["work_" + key].tolist(), key
     for hist, ref in zip(out["residuals"], g["residuals"]):
         ref = ref[~np.isnan(ref)]
-        np.testing.assert_allclose(hist, ref, rtol=1e-9)
-    assert _relerr(out["uend"], g["uend"]) < 1e-14
+        # (atol: numpy's dot may split long vectors over BLAS threads, which moves the CG iterates by an ulp or two)
+        np.testing.assert_allclose(hist, ref, rtol=1e-9, atol=1e-14)
+    if "uend" in g:
+        assert _relerr(out["uend"], g["uend"]) < 1e-14
+    else:
+        sub = spec["subsample"]
+        assert _relerr(out["uend"][::sub, ::sub], g["uend_sub"]) < 1e-13
 
 
 def test_reference_known_answers():

@@ -1,32 +1,50 @@
-"""Drop-in check inside the UNMODIFIED reference (build container only: needs /root/reference): pySDC's own
-controller_nonMPI, Step, Level, hooks and convergence controllers drive the classes of pysdc_b200.pysdc_plugin selected
-purely through the description dict.  The kernel library is replaced by the numpy test double (no GPU here); the GPU
-suite runs the same sweepers / problems against the real kernels."""
+"""Drop-in check inside the UNMODIFIED reference: pySDC's own controller_nonMPI, Step, Level, hooks and convergence
+controllers drive the classes of pysdc_b200.pysdc_plugin selected purely through the description dict.
+
+Two variants of every test: ``numpy`` — the kernel library replaced by the numpy test double (CPU suite, host logic
+only) — and ``cuda`` (``-m gpu``) — the reference's controller on the REAL CUDA kernels through the C ABI.  The
+reference is imported from /root/reference in the build container and from the shipped copy ``oracle/_ref`` on the GPU
+box (oracle/build_ref.py; verified against its manifest)."""
 import os
 import sys
 
 import numpy as np
 import pytest
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, reference_paths
 
-REF = os.environ.get("PYSDC_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pySDC")), reason="reference tree not present")
+REF_PATHS = reference_paths()
+pytestmark = pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
 
 
-@pytest.fixture()
-def plugin():
-    sys.path.insert(0, os.path.join(ROOT, "oracle", "qmat_shim"))
-    sys.path.insert(0, REF)
-    from fake_backend import NumpyBackend
+@pytest.fixture(params=["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+def plugin(request):
+    for p in reversed(REF_PATHS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
     from pysdc_b200 import backend
 
     old = backend._backend
-    backend.set_backend(NumpyBackend())
+    if request.param == "cuda":
+        backend.set_backend(backend.CudaBackend())
+    else:
+        from fake_backend import NumpyBackend
+
+        backend.set_backend(NumpyBackend())
     from pysdc_b200 import pysdc_plugin
 
     yield pysdc_plugin
     backend.set_backend(old)
+
+
+def test_shipped_reference_is_unmodified():
+    """oracle/_ref (when present) is byte-identical to what oracle/build_ref.py copied from the reference tree."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build_ref
+
+    if not os.path.isfile(build_ref.MANIFEST):
+        pytest.skip("oracle/_ref not built")
+    assert build_ref.verify()
 
 
 @pytest.mark.parametrize("name", ["run_heat3d_gi_minsrns_31", "run_heat3d_gi_lu_31", "run_heat2d_imex_lu_63",
