@@ -135,7 +135,7 @@ def test_second_residual_request_is_answered_from_the_first():
             L.params.residual_type = "last_abs"
         L.sweep.compute_residual()
         assert be.launches > n0, change
-        assert L.status.residual != second or change == "tau", change  # (the max may sit on another node)
+        assert L.status.residual != second or change in ("tau", "rtype"), change  # (the max may sit on another node)
         second = L.status.residual
     n0 = be.launches
     L.sweep.compute_residual()
