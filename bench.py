@@ -1,13 +1,24 @@
 #!/usr/bin/env python
-"""Headline benchmark: SDC sweep DOF-node updates/s on the configuration BASELINE.json quotes
-(3-D heat 511^3 fp64, generic_implicit, M=4 RADAU-RIGHT nodes, QI='MIN-SR-NS' -> node-batched solves).
+"""Benchmark of the SDC sweep path: DOF-node updates/s on the configurations BASELINE.json names.
 
-    python bench.py --gpus 1 --steps 3 --warmup 3                 # this repo's CUDA path
-    python bench.py --impl reference --steps 1 --warmup 0         # the reference algorithm on the host cores
+    python bench.py --gpus 1 --steps 3 --warmup 3                 # headline: config 3 (3-D heat 511^3, M=4 MIN-SR-NS)
+    python bench.py --config 2|4                                  # 2-D forced heat 2047^2 IMEX LU / Allen-Cahn 2048^2
+    torchrun ... bench.py --gpus 8 [--config 5]                   # slab-sharded config 3 / PFASST, one slice per GPU
+    python bench.py --impl reference --steps 20 --warmup 5        # the UNMODIFIED reference on the host cores
 
-One "step" = one SDC time step on a fresh seeded random field: predict + K=4 x (update_nodes + compute_residual) +
-compute_end_point, i.e. N*M*4 DOF-node updates.  Prints ONE JSON line (contract in the task description; field meanings
-in DESIGN.md section "Measurement").
+One "step" = one SDC time step of the configuration through a controller: predict + sweeps (update_nodes +
+compute_residual each) + compute_end_point; DOF-node updates per step = N * M * sweeps.  Prints ONE JSON line
+(contract in the task description; field meanings in DESIGN.md section "Measurement").
+
+Legs of the default arm:
+  value      inputs resident in HBM, CUDA events around K steps, max over ranks
+  e2e        the same steps through the reference-facing API with HOST buffers: pySDC's own controller_nonMPI (the
+             unmodified reference, oracle/_ref) drives the plug-in classes; every step copies its input from pinned host
+             memory and its result back
+  roofline   the dominant kernel (persistent CG / Newton launch): algorithmic bytes per launch / CUDA-event time
+  check      the answer: residual after every sweep and |uend| against a committed record of this very run
+             (tests/golden/bench_record_*.json) - a wrong answer fails the bench (exit code 3)
+  cpu_baseline (N=1)  the reference's own classes timed on this host on a bounded sample
 """
 import argparse
 import json
@@ -22,33 +33,66 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-M_NODES, K_SWEEPS = 4, 4
-METRIC = "SDC sweep DOF-node updates/s (3D heat 511^3, M=4 MIN-SR-NS, fp64)"
 UNIT = "DOF-node updates/s"
+HEADLINE_METRIC = "SDC sweep DOF-node updates/s (3D heat 511^3, M=4 MIN-SR-NS, fp64)"
 
 
-def spec_for(n, K=K_SWEEPS):
-    """Description of the headline workload for an n^3 grid, as a fixture-style spec."""
-    return dict(problem="heatNd_unforced", sweeper="generic_implicit",
-                problem_params=dict(nvars=[n, n, n], nu=0.1, freq=[1, 1, 1], bc="dirichlet-zero", solver_type="CG",
-                                    lintol=1e-12, liniter=10000),
-                sweeper_params=dict(num_nodes=M_NODES, quad_type="RADAU-RIGHT", QI="MIN-SR-NS", initial_guess="spread"),
-                level_params=dict(dt=1e-3, restol=-1.0), step_params=dict(maxiter=K),
-                t0=0.0, Tend=1e-3, u0="random", seed=1234)
+# ---------------------------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------------------------
+def workload(config, n=None):
+    """Fixture-style description of BASELINE config `config` on an n-point grid (None: the BASELINE size)."""
+    if config == 3:
+        n = n or 511
+        return dict(config=3, n=n, name=f"heat3d_{n}cubed_M4_MINSRNS_K4", metric=HEADLINE_METRIC if n == 511 else
+                    f"SDC sweep DOF-node updates/s (3D heat {n}^3, M=4 MIN-SR-NS, fp64)",
+                    problem="heatNd_unforced", sweeper="generic_implicit",
+                    problem_params=dict(nvars=(n, n, n), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", solver_type="CG",
+                                        lintol=1e-12, liniter=10000),
+                    sweeper_params=dict(num_nodes=4, quad_type="RADAU-RIGHT", QI="MIN-SR-NS", initial_guess="spread"),
+                    level_params=dict(dt=1e-3, restol=-1.0), step_params=dict(maxiter=4), dt=1e-3, u0="random",
+                    seed=1234, M=4, ndof=n**3, inputs="seeded N(0,1) field, default_rng(1234)")
+    if config == 2:
+        n = n or 2047
+        return dict(config=2, n=n, name=f"heat2d_forced_{n}sq_imex_M4_LU",
+                    metric=f"SDC sweep DOF-node updates/s (2D forced heat {n}^2, IMEX M=4 LU, restol 1e-10, fp64)",
+                    problem="heatNd_forced", sweeper="imex_1st_order",
+                    problem_params=dict(nvars=(n, n), nu=0.1, freq=(4, 4), bc="dirichlet-zero", solver_type="CG",
+                                        lintol=1e-12, liniter=10000),
+                    sweeper_params=dict(num_nodes=4, quad_type="RADAU-RIGHT", QI="LU"),
+                    level_params=dict(dt=0.1, restol=1e-10), step_params=dict(maxiter=50), dt=0.1, u0="exact", M=4,
+                    ndof=n**2, inputs="u_exact(0)")
+    if config == 4:
+        n = n or 2048
+        return dict(config=4, n=n, name=f"allencahn_{n}sq_fullyimplicit_M3_LU",
+                    metric=f"SDC sweep DOF-node updates/s (2D Allen-Cahn {n}^2 fully implicit, M=3 LU, restol 1e-8, fp64)",
+                    problem="allencahn_fullyimplicit", sweeper="generic_implicit",
+                    problem_params=dict(nvars=(n, n), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9,
+                                        lin_tol=1e-10, lin_maxiter=100, radius=0.25),
+                    sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU", initial_guess="zero"),
+                    level_params=dict(dt=1e-3, restol=1e-8), step_params=dict(maxiter=50), dt=1e-3, u0="exact", M=3,
+                    ndof=n**2, inputs="u_exact(0) (tanh circle)")
+    if config == 5:
+        n = n or 1023
+        return dict(config=5, n=n, name=f"pfasst_heat2d_forced_{n}sq_{n // 2}sq_imex_M3_LU",
+                    metric=f"SDC sweep DOF-node updates/s (PFASST 2-level 2D forced heat {n}^2/{n // 2}^2, one slice per GPU, fp64)",
+                    problem="heatNd_forced", sweeper="imex_1st_order",
+                    problem_params=dict(nvars=[(n, n), (n // 2, n // 2)], nu=0.1, freq=(4, 4), bc="dirichlet-zero",
+                                        solver_type="CG", lintol=1e-12, liniter=10000),
+                    sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+                    level_params=dict(dt=0.25, restol=1e-10), step_params=dict(maxiter=50),
+                    space_transfer_params=dict(rorder=2, iorder=6), dt=0.25, u0="exact", M=3, ndof=n**2,
+                    inputs="u_exact(0)")
+    raise SystemExit(f"unknown config {config}")
 
 
-def measured_traffic(n, world):
-    """Mean DRAM bytes per CG launch from the committed ncu capture of this very command (profiles/): only meaningful
-    for the configuration it was taken on (511^3, one GPU)."""
-    try:
-        if n != 511 or world != 1:
-            return None, None
-        with open(os.path.join(ROOT, "profiles", "cg_traffic_511.json")) as f:
-            t = json.load(f)
-        per = [l["traffic"] for l in t["launches"]]
-        return float(np.mean(per)), "profiles/cg_traffic_511.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of 8 launches)"
-    except Exception:
-        return None, None
+def description(w, classes, transfer=None, **extra_problem_params):
+    d = dict(problem_class=classes[w["problem"]], problem_params=dict(w["problem_params"], **extra_problem_params),
+             sweeper_class=classes[w["sweeper"]], sweeper_params=dict(w["sweeper_params"]),
+             level_params=dict(w["level_params"]), step_params=dict(w["step_params"]))
+    if "space_transfer_params" in w:
+        d.update(space_transfer_class=transfer, space_transfer_params=dict(w["space_transfer_params"]))
+    return d
 
 
 def peaks():
@@ -58,6 +102,22 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(w, world):
+    """Mean DRAM bytes per launch of the dominant kernel from the committed ncu capture of this very command
+    (profiles/): only meaningful for the configuration it was taken on."""
+    try:
+        name = {3: "cg_traffic_511.json", 2: "cg_traffic_config2.json", 4: "newton_traffic_config4.json"}[w["config"]]
+        if world != 1 or w["n"] != workload(w["config"])["n"]:
+            return None, None
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            t = json.load(f)
+        per = [l["traffic"] for l in t["launches"]]
+        return float(np.mean(per)), (f"profiles/{name} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean of "
+                                     f"{len(per)} launches)")
+    except Exception:
+        return None, None
 
 
 class ClockSampler:
@@ -103,55 +163,204 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the oracle restatement of the reference algorithm (scipy sparse + scipy cg)
+# the reference itself (oracle/_ref = the unmodified pySDC package, oracle/build_ref.py) on the host cores
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(n, K):
-    """One SDC step of the headline description at n^3 with the oracle port; the sparse operator is assembled outside
-    the timed region (the reference does that in the problem constructor)."""
+def reference_modules():
+    """Import the UNMODIFIED reference (+ the qmat stand-in).  Returns None when no copy of it is available."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import sdc_oracle
+    import build_ref
 
-    spec = spec_for(n, K)
+    paths = build_ref.reference_paths()
+    if paths is None:
+        return None
+    for p in reversed(paths):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+    from pySDC.implementations.hooks.log_work import LogWork
+    from pySDC.implementations.problem_classes.AllenCahn_2D_FD import allencahn_fullyimplicit
+    from pySDC.implementations.problem_classes.HeatEquation_ND_FD import heatNd_forced, heatNd_unforced
+    from pySDC.implementations.sweeper_classes.generic_implicit import generic_implicit
+    from pySDC.implementations.sweeper_classes.imex_1st_order import imex_1st_order
+    from pySDC.implementations.transfer_classes.TransferMesh import mesh_to_mesh
+
+    return dict(controller_nonMPI=controller_nonMPI, get_sorted=get_sorted, LogWork=LogWork, mesh_to_mesh=mesh_to_mesh,
+                classes=dict(heatNd_unforced=heatNd_unforced, heatNd_forced=heatNd_forced,
+                             allencahn_fullyimplicit=allencahn_fullyimplicit, generic_implicit=generic_implicit,
+                             imex_1st_order=imex_1st_order),
+                where=paths[-1])
+
+
+class ReferenceRun:
+    """The reference's own classes and controller on one workload: set-up (sparse operator assembly, done by the
+    reference in the problem constructor) outside the timed steps."""
+
+    def __init__(self, w, num_procs=1):
+        self.ref = reference_modules()
+        if self.ref is None:
+            raise RuntimeError("no copy of the reference (oracle/_ref missing: run __graft_entry__.build() in the build "
+                               "container)")
+        self.w = w
+        t0 = time.perf_counter()
+        d = description(w, self.ref["classes"], transfer=self.ref["mesh_to_mesh"])
+        cp = dict(logger_level=40, hook_class=[self.ref["LogWork"]])
+        if w["config"] == 5:
+            cp["predict_type"] = "pfasst_burnin"
+        self.ctrl = self.ref["controller_nonMPI"](num_procs=num_procs, controller_params=cp, description=d)
+        self.num_procs = num_procs
+        self.P = self.ctrl.MS[0].levels[0].prob
+        if w["u0"] == "random":
+            self.u0 = self.P.u_init
+            self.u0[:] = np.random.default_rng(w["seed"]).standard_normal(w["problem_params"]["nvars"])
+        else:
+            self.u0 = self.P.u_exact(0.0)
+        self.setup_seconds = time.perf_counter() - t0
+
+    def step(self):
+        w, gs = self.w, self.ref["get_sorted"]
+        t0 = time.perf_counter()
+        uend, stats = self.ctrl.run(u0=self.u0, t0=0.0, Tend=w["dt"] * self.num_procs)
+        secs = time.perf_counter() - t0
+        niter = [int(v) for _, v in gs(stats, type="niter", sortby="time")]
+        work = {k: sum(int(v) for _, v in gs(stats, type="work_" + k)) for k in self.P.work_counters}
+        return dict(seconds=secs, sweeps=sum(niter), niter=niter, work=work, updates=w["ndof"] * w["M"] * sum(niter),
+                    uend_maxabs=float(abs(uend)))
+
+
+def describe_work(w, r):
+    if "CG" in r["work"]:
+        solves = max(r["sweeps"] * w["M"], 1)
+        return f"{r['work']['CG'] / solves:.1f} CG it/solve"
+    return f"{r['work'].get('newton', 0)} Newton / {r['work'].get('linear', 0)} linear its per step"
+
+
+REF_SIZES = {3: [255, 191, 127, 95, 63, 31], 2: [2047, 1023, 511, 255], 4: [2048, 1024, 512, 256, 128],
+             5: [1023, 511, 255, 127]}
+CALIB_SIZE = {3: 47, 2: 255, 4: 128, 5: 127}
+# growth of the cost per DOF-node update with the grid (the CG iteration count per solve grows with n; the reference is
+# memory-bound beyond the host caches): single-core probes in the build container, used only to pick the sample size
+REF_GROWTH = {3: lambda n: 1 + n / 64.0, 2: lambda n: 1 + n / 90.0, 4: lambda n: 1.0 + n / 512.0,
+              5: lambda n: 1 + n / 128.0}
+
+
+def pick_ref_size(config, steps_total, budget_s):
+    """Largest grid whose `steps_total` reference steps (plus operator assembly) are expected to fit `budget_s`: one
+    step on a small grid calibrates this host's speed, the measured cost per DOF-node update is scaled with the
+    growth law above."""
+    nc = CALIB_SIZE[config]
+    wc = workload(config, nc)
     t0 = time.perf_counter()
-    L = sdc_oracle.make_level(spec)
-    t_setup = time.perf_counter() - t0
-    u0 = sdc_oracle.initial_value(L.prob, spec)
-    t0 = time.perf_counter()
-    out = sdc_oracle.run_sdc(spec, u0=u0, level=L)
-    secs = time.perf_counter() - t0
-    return dict(rate=n**3 * M_NODES * K / secs, seconds=secs, setup_seconds=t_setup, n=n, K=K,
-                cg_per_solve=out["work"]["CG"][0] / (M_NODES * K))
+    run = ReferenceRun(wc, num_procs=8 if config == 5 else 1)
+    r = run.step()
+    per_update = r["seconds"] / r["updates"] / REF_GROWTH[config](nc)
+    setup_per_dof = run.setup_seconds / wc["ndof"]
+    spent = time.perf_counter() - t0
+    for n in REF_SIZES[config]:
+        w = workload(config, n)
+        per_step = per_update * REF_GROWTH[config](n) * w["ndof"] * w["M"] * r["sweeps"]
+        if 2.0 * setup_per_dof * w["ndof"] + steps_total * per_step <= budget_s - spent:
+            return n
+    return REF_SIZES[config][-1]
 
 
 def run_reference(args):
-    n = args.ref_n
+    """`--impl reference`: K timed steps of the UNMODIFIED reference (its own classes, controller, scipy solvers) on the
+    box's host cores.  The 511^3 workload itself is out of reach of the reference (it assembles a 934 M-nnz sparse
+    matrix and needs ~7 s per CG iteration): each step is the same description on a smaller grid - the bounded sample -
+    chosen as the largest one whose W+K steps fit the time budget."""
     t_all = time.perf_counter()
-    rates = []
-    # bounded: every step is ~10-25 s of single-core work; at most one untimed warm-up step and ~2.5 minutes in total
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_rate(n, K_SWEEPS)
-    for _ in range(max(args.steps, 1)):
-        rates.append(cpu_reference_rate(n, K_SWEEPS))
-        if time.perf_counter() - t_all > 150.0:
-            break
-    secs = sum(r["seconds"] for r in rates)
-    value = n**3 * M_NODES * K_SWEEPS * len(rates) / secs
-    sample = (f"oracle port of the reference path (scipy sparse matvec + scipy cg), same description at {n}^3 "
-              f"(bounded sample of the 511^3 workload), {K_SWEEPS} sweeps/step, {rates[0]['cg_per_solve']:.1f} CG it/solve")
-    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(rates),
-                warmup=args.warmup, ms_per_step=1e3 * secs / len(rates), higher_is_better=True, scaling="weak",
+    full = workload(args.config)
+    n = args.ref_n or pick_ref_size(args.config, args.steps + args.warmup, args.ref_budget)
+    w = workload(args.config, n)
+    run = ReferenceRun(w, num_procs=8 if args.config == 5 else 1)
+    for _ in range(args.warmup):
+        run.step()
+    cpu0 = time.process_time()
+    steps = [run.step() for _ in range(args.steps)]
+    secs = sum(r["seconds"] for r in steps)
+    cores = max(1, int(round((time.process_time() - cpu0) / secs)))  # numpy's BLAS may thread its level-1 calls
+    value = sum(r["updates"] for r in steps) / secs
+    where = run.ref["where"]
+    where = os.path.relpath(where, ROOT) if where.startswith(ROOT) else where
+    sample = (f"unmodified reference classes ({w['problem']}, {w['sweeper']}, controller_nonMPI; scipy sparse matvec + "
+              f"scipy cg; process CPU time / wall = {cores}) from {where}; same description at n={n} (bounded sample of the n={full['n']} "
+              f"workload: {w['name']}), {steps[0]['sweeps']} sweeps/step, {describe_work(w, steps[0])}, operator assembly "
+              f"{run.setup_seconds:.1f} s outside the timed steps; host has {os.cpu_count()} cores")
+    line = dict(impl="reference", metric=full["metric"], value=value, unit=UNIT, n_gpus=args.gpus, steps=len(steps),
+                warmup=args.warmup, ms_per_step=1e3 * secs / len(steps), higher_is_better=True, scaling="strong",
                 vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload=f"heat3d_{n}cubed_M4_MINSRNS_K{K_SWEEPS} (CPU sample of heat3d_511cubed)",
-                            inputs="seeded N(0,1) field, default_rng(1234)"),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind="port", sample=sample),
+                config=dict(workload=full["name"], inputs=full["inputs"], sample_workload=w["name"]),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="reference", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                wall_s=time.perf_counter() - t_all)
+                niter=steps[0]["niter"], uend_maxabs=steps[0]["uend_maxabs"], wall_s=time.perf_counter() - t_all)
     print(json.dumps(line))
+
+
+def cpu_baseline(w_full, budget_s):
+    """cpu_baseline of the default arm: ONE step of the reference's own classes on a bounded sample (about `budget_s`
+    seconds of single-core work)."""
+    cfg = w_full["config"]
+    n = pick_ref_size(cfg, 1, budget_s)
+    w = workload(cfg, n)
+    run = ReferenceRun(w, num_procs=8 if cfg == 5 else 1)
+    cpu0 = time.process_time()
+    r = run.step()
+    cores = max(1, int(round((time.process_time() - cpu0) / r["seconds"])))
+    return dict(value=r["updates"] / r["seconds"], unit=UNIT, cores=cores, kind="reference",
+                sample=(f"unmodified reference classes ({w['problem']}, {w['sweeper']}, controller_nonMPI; scipy sparse "
+                        f"matvec + scipy cg; process CPU time / wall = {cores}) on this host, same description at n={n} ({w['name']}), 1 step "
+                        f"of {r['sweeps']} sweeps in {r['seconds']:.1f} s (+ {run.setup_seconds:.1f} s operator assembly), "
+                        f"{describe_work(w, r)}; host has {os.cpu_count()} cores"))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ---------------------------------------------------------------------------------------------------------------------
+def record_path(w, world):
+    tag = f"config{w['config']}_n{w['n']}" + (f"_p{world}" if w["config"] == 5 else "")
+    return os.path.join(ROOT, "tests", "golden", f"bench_record_{tag}.json")
+
+
+def check_answer(w, world, residuals, niter, uend_maxabs, write=False):
+    """Compare the run's answer with the committed single-GPU record of the same workload: residual after every sweep
+    to 1e-6 relative (+ the solver noise floor), |uend| to 1e-10 relative, SDC iteration counts identical."""
+    path = record_path(w, world)
+    got = dict(niter=niter, residuals=residuals, uend_maxabs=uend_maxabs)
+    if write:
+        with open(path, "w") as f:
+            json.dump(dict(workload=w["name"], note="written by `bench.py --write-record` on one B200", **got), f, indent=1)
+        return dict(status="recorded", record=os.path.relpath(path, ROOT))
+    if not os.path.exists(path):
+        return dict(status="no record", record=os.path.relpath(path, ROOT))
+    with open(path) as f:
+        ref = json.load(f)
+    ok = niter == ref["niter"]
+    dres = 0.0
+    for a, b in zip(residuals, ref["residuals"]):
+        ok = ok and len(a) == len(b)
+        for x, y in zip(a, b):
+            dres = max(dres, abs(x - y) / max(abs(y), 1e-300))
+            ok = ok and abs(x - y) <= 1e-6 * abs(y) + 2e-11 * max(1.0, ref["uend_maxabs"])
+    duend = abs(uend_maxabs - ref["uend_maxabs"]) / ref["uend_maxabs"]
+    ok = ok and duend <= 1e-10
+    return dict(status="ok" if ok else "MISMATCH", record=os.path.relpath(path, ROOT), niter=niter,
+                niter_record=ref["niter"], max_rel_residual_diff=dres, rel_uend_maxabs_diff=duend,
+                against="single-GPU record of the same workload")
+
+
+def algorithmic_bytes(w, nloc, counters):
+    """SURVEY.md section 8d, per launch of the dominant kernel.  Heat CG: 8 B * N * sum_b (4 [set-up: read b, x0; write
+    r, p] + 9 * iterations_b).  Allen-Cahn Newton: per Newton step g (read u, rhs; write g: 3), Jacobian diagonal (read
+    u, write d: 2), CG set-up (4), update u -= z (3) and 10 streams per linear iteration (9 + the diagonal); one more
+    residual evaluation (3) ends the solve."""
+    c = np.asarray(counters, dtype=np.int64)
+    if w["config"] == 4:
+        newton, linear = c[..., 0], c[..., 1]
+        return 8.0 * nloc * float(np.sum(12 * newton + 3 + 10 * linear))
+    return 8.0 * nloc * float(np.sum(4 + 9 * c))
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -164,56 +373,78 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from pysdc_b200 import backend as bk
+    from pysdc_b200 import problems, sweepers
     from pysdc_b200.controller import controller_nonMPI
-    from pysdc_b200.problems import heatNd_unforced
-    from pysdc_b200.sweepers import generic_implicit
+    from pysdc_b200.stats import get_sorted
 
     be = bk.get_backend()
-    n = args.n
-    spec = spec_for(n)
-    pp = dict(spec["problem_params"])
-    pp["nvars"], pp["freq"] = tuple(pp["nvars"]), tuple(pp["freq"])
+    w = workload(args.config, args.n)
+    n = w["n"]
+    own = dict(heatNd_unforced=problems.heatNd_unforced, heatNd_forced=problems.heatNd_forced,
+               allencahn_fullyimplicit=problems.allencahn_fullyimplicit, generic_implicit=sweepers.generic_implicit,
+               imex_1st_order=sweepers.imex_1st_order)
+    extra = {}
     if args.precond:
-        pp["preconditioner"] = "chebyshev"
+        extra["preconditioner"] = "chebyshev"
     comm = None
-    if world > 1:
+    pfasst = w["config"] == 5
+    if world > 1 and not pfasst:
+        if w["config"] != 3:
+            raise SystemExit("multi-GPU runs: config 3 (slab-decomposed) or config 5 (PFASST)")
         # the SAME n^3 problem, slab-decomposed along axis 0 over the GPUs of the node ("strong" scaling)
         from pysdc_b200.parallel import SlabComm
 
         comm = SlabComm()
-        pp["comm"] = comm
-    description = dict(problem_class=heatNd_unforced, problem_params=pp, sweeper_class=generic_implicit,
-                       sweeper_params=dict(spec["sweeper_params"]), level_params=dict(spec["level_params"]),
-                       step_params=dict(spec["step_params"]))
-    ctrl = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40}, description=description)
-    P = ctrl.MS[0].levels[0].prob
-
-    # seeded N(0,1) field of the global grid, generated on the host plane by plane; a rank keeps the planes it owns
-    lay = P._lay
-    nz, z0 = (lay.nz, lay.z0) if lay.is_slab else (n, 0)
-    rng = np.random.default_rng(1234)
-    host_u0 = torch.empty((nz, n, n), dtype=torch.float64).pin_memory()
-    for z in range(z0 + nz):
-        plane = rng.standard_normal((n, n))
-        if z >= z0:
-            host_u0.numpy()[z - z0] = plane
-    host_uend = torch.empty((nz, n, n), dtype=torch.float64).pin_memory()
-    u0 = P.dtype_u(P.init)
-    u0.data.copy_(host_u0, non_blocking=True)
-    dof_updates_per_step = n**3 * M_NODES * K_SWEEPS  # of the whole job, whatever the number of GPUs
-
-    def step():
-        return ctrl.run(u0=u0, t0=0.0, Tend=1e-3)
+        extra["comm"] = comm
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    if pfasst:
+        # one time slice per rank/GPU; a step = one block of `world` slices
+        from pysdc_b200.parallel import LocalComm, TorchComm
+        from pysdc_b200.pfasst import controller_MPI
+        from pysdc_b200.transfer import mesh_to_mesh
+
+        tcomm = TorchComm() if world > 1 else LocalComm()
+        ctrl = controller_MPI(dict(logger_level=40, predict_type="pfasst_burnin"),
+                              description(w, own, transfer=mesh_to_mesh), comm=tcomm)
+        levels = ctrl.S.levels
+    else:
+        ctrl = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40},
+                                 description=description(w, own, **extra))
+        levels = ctrl.MS[0].levels
+    L = levels[0]
+    P = L.prob
+    Tend = w["dt"] * (world if pfasst else 1)
+
+    # the step's input in pinned host memory (a rank keeps the planes of its slab), generated plane by plane
+    lay = P._lay
+    if w["u0"] == "random":
+        nz, z0 = (lay.nz, lay.z0) if lay.is_slab else (n, 0)
+        rng = np.random.default_rng(w["seed"])
+        host_in = torch.empty((nz, n, n), dtype=torch.float64).pin_memory()
+        for z in range(z0 + nz):
+            plane = rng.standard_normal((n, n))
+            if z >= z0:
+                host_in.numpy()[z - z0] = plane
+    else:
+        host_in = torch.from_numpy(np.ascontiguousarray(P.u_exact(0.0).get())).pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    nloc = int(np.prod(host_in.shape))
+    u0 = P.dtype_u(P.init)
+    u0.data.copy_(host_in, non_blocking=True)
+
+    def step(c, u):
+        return c.run(u0=u, t0=0.0, Tend=Tend)
+
     for _ in range(args.warmup):
-        step()
+        step(ctrl, u0)
     # ---- device-resident timing -------------------------------------------------------------------------------------
-    P.solve_log = []
+    for lvl in levels:
+        lvl.prob.solve_log = []
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -222,40 +453,79 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        uend, stats = step()
+        uend, stats = step(ctrl, u0)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = be.launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    solve_log, P.solve_log = P.solve_log, None
+    fine_log = list(L.prob.solve_log)
+    coarse_log = [e for lvl in levels[1:] for e in lvl.prob.solve_log]
+    ncoarse = int(np.prod(levels[1].prob.nvars)) if len(levels) > 1 else 0
+    for lvl in levels:
+        lvl.prob.solve_log = None
+    niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
+    times = [t for t, _ in get_sorted(stats, type="niter", sortby="time")]
+    residuals = [[float(v) for _, v in get_sorted(stats, time=t, level=0, type="residual_post_iteration", sortby="iter")]
+                 for t in times]
+    uend_maxabs = float(abs(uend))
+    if pfasst and world > 1:
+        gathered = tcomm.allgather((niter, residuals))
+        niter = [v for g in gathered for v in g[0]]
+        residuals = [r for g in gathered for r in g[1]]
+    sweeps_per_step = sum(niter)
+    updates_per_step = w["ndof"] * w["M"] * sweeps_per_step  # of the whole job, whatever the number of GPUs
 
-    # ---- end to end through the public API with host buffers --------------------------------------------------------
+    # ---- end to end through the reference-facing API with host buffers ----------------------------------------------
+    e2e_ctrl, e2e_via = ctrl, "pysdc_b200's stand-alone controller"
+    ref = None if (pfasst or args.no_reference_controller) else reference_modules()
+    if ref is not None:
+        # pySDC's OWN controller_nonMPI, Step, Level, hooks and convergence controllers (unmodified) drive the plug-in
+        # classes: exactly what a pySDC user gets after changing the two import lines of INTEGRATION.md
+        from pysdc_b200 import pysdc_plugin as plug
+
+        pc = dict(heatNd_unforced=plug.heatNd_unforced, heatNd_forced=plug.heatNd_forced,
+                  allencahn_fullyimplicit=plug.allencahn_fullyimplicit, generic_implicit=plug.generic_implicit,
+                  imex_1st_order=plug.imex_1st_order)
+        del ctrl, levels, L, P
+        e2e_ctrl = ref["controller_nonMPI"](num_procs=1, controller_params={"logger_level": 40},
+                                            description=description(w, pc, **extra))
+        e2e_via = "pySDC controller_nonMPI (unmodified reference, oracle/_ref) driving pysdc_b200.pysdc_plugin classes"
+        P2 = e2e_ctrl.MS[0].levels[0].prob
+        u0 = P2.dtype_u(P2.init)
+        u0.data.copy_(host_in, non_blocking=True)
+        for _ in range(min(args.warmup, 2)):
+            step(e2e_ctrl, u0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     copy_stream = torch.cuda.Stream()
     for _ in range(args.steps):
-        u0.data.copy_(host_u0, non_blocking=True)           # H2D of the step's input from pinned memory
-        uend, stats = step()
+        u0.data.copy_(host_in, non_blocking=True)           # H2D of the step's input from pinned memory
+        uend2, stats2 = step(e2e_ctrl, u0)
         # D2H of the step's result on a side stream: it overlaps the next step's compute (uend is a fresh buffer per
         # step); the timed region ends only after the last copy has landed
         copy_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(copy_stream):
-            host_uend.copy_(uend.data, non_blocking=True)
-            uend.data.record_stream(copy_stream)
+            host_out.copy_(uend2.data, non_blocking=True)
+            uend2.data.record_stream(copy_stream)
     torch.cuda.current_stream().wait_stream(copy_stream)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    e2e_uend_maxabs = float(abs(uend2))
+    gs2 = ref["get_sorted"] if ref is not None else get_sorted
+    niter2 = [int(v) for _, v in gs2(stats2, type="niter", sortby="time")]
+    if pfasst and world > 1:
+        niter2 = [v for g in tcomm.allgather(niter2) for v in g]
+    e2e_consistent = niter2 == niter and abs(e2e_uend_maxabs - uend_maxabs) <= 1e-10 * uend_maxabs
 
     # ---- the streaming kernels of the sweep on their own (north_star: "collocation integration ... one coalesced
     # kernel fused with the rhs assembly and the residual norm"): algorithmic bytes / CUDA-event time ----------------
     other = {}
-    if rank == 0 and world == 1:
-        L = ctrl.MS[0].levels[0]
-        sweep = L.sweep
-        nloc = nz * n * n
+    if rank == 0 and world == 1 and w["config"] == 3:
+        Lx = e2e_ctrl.MS[0].levels[0]
+        Px, sweep, M = Lx.prob, Lx.sweep, w["M"]
         reps = 10
 
         def timed(fn):
@@ -268,18 +538,18 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
 
-        fins = sweep._f_inputs(L)
-        rhs = sweep._scratch(L, M_NODES)
-        W = np.random.default_rng(0).standard_normal((M_NODES, len(fins)))
-        norms = be.zeros(M_NODES)
+        fins = sweep._f_inputs(Lx)
+        rhs = sweep._scratch(Lx, M)
+        W = np.random.default_rng(0).standard_normal((M, len(fins)))
+        norms = be.zeros(M)
         kernels = {
-            "colloc_sweep_kernel<4,1> (rhs assembly: u0 + dt(Q-QD)F)":
-                (lambda: be.colloc_sweep(fins, 1, [r.flat for r in rhs], Wq=W, Wi=-W, base=L.u[0].flat), 8 * (2 * M_NODES + 1)),
+            "colloc_sweep_kernel<4,1> (rhs assembly: u0 + dt Q F - dt QD F, reference rounding)":
+                (lambda: be.colloc_sweep(fins, 1, [r.flat for r in rhs], Wq=W, Wi=-W, base=Lx.u[0].flat), 8 * (2 * M + 1)),
             "colloc_residual_kernel<4,1> (residual + max-norms)":
-                (lambda: be.colloc_residual(W, fins, 1, L.u[0].flat, [u.flat for u in L.u[1:]], None, None, norms),
-                 8 * (2 * M_NODES + 1)),
+                (lambda: be.colloc_residual(W, fins, 1, Lx.u[0].flat, [u.flat for u in Lx.u[1:]], None, None, norms),
+                 8 * (2 * M + 1)),
             "eval_f_kernel<3> (4 fields)":
-                (lambda: P.eval_f_batch(L.u[1:], [0.0] * M_NODES, L.f[1:]), 16 * M_NODES),
+                (lambda: Px.eval_f_batch(Lx.u[1:], [0.0] * M, Lx.f[1:]), 16 * M),
         }
         for name, (fn, bytes_per_dof) in kernels.items():
             t_ms = timed(fn)
@@ -291,55 +561,78 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = (float(v) for v in t.tolist())
 
+    rc = 0
     if rank == 0:
         peak, peak_src = peaks()
-        # dominant kernel: the persistent batched CG.  Algorithmic bytes per launch:
-        # sum over the B systems of 8 B * N * (4 [set-up: read b, x0; write r, p] + 9 * iterations)
-        cg_ms = sum(a.elapsed_time(b) for a, b, _ in solve_log)
-        cg_iters = torch.stack([c for _, _, c in solve_log]).cpu().numpy().astype(np.int64)
-        # plain CG: 4 streams of set-up + 9 per iteration; the polynomial preconditioner adds one pass (read r, write z)
-        per_it, setup = (11, 6) if args.precond else (9, 4)
-        alg_bytes = 8.0 * nz * n * n * float(np.sum(setup + per_it * cg_iters))  # this rank's share
+        # dominant kernel: the persistent solver launches (batched CG / Newton).  Their CUDA-event time on the launching
+        # stream and the iteration counters they left on the device give achieved = algorithmic bytes / time.
+        solve_log = fine_log + coarse_log
+        k_ms = sum(a.elapsed_time(b) for a, b, _ in solve_log)
         n_launch = len(solve_log)
-        achieved = alg_bytes / (cg_ms * 1e-3) / 1e9
-        n_cg = float(cg_iters.mean())
-        b_alg = 84 + (16 + 88 * n_cg if args.precond else 72 * n_cg)
-        traffic, traffic_src = (None, None) if args.precond else measured_traffic(n, world)
-        value = dof_updates_per_step * args.steps / (ms * 1e-3)
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong" if world > 1 else "weak",
-                    vs_baseline=None,
-                    dtype="f64", data="synthetic",
-                    config=dict(workload=f"heat3d_{n}cubed_M4_MINSRNS_K{K_SWEEPS}", parallelism=f"{world} slabs along axis 0 (peer-memory CG)" if world > 1 else "single GPU",
-                                cache="working set per step ~28 GB >> 126 MB L2: no flush needed",
-                                inputs="seeded N(0,1) field, default_rng(1234)", cg_it_per_solve=n_cg,
-                                solver=("CG preconditioned with a degree-1 Chebyshev polynomial of the operator "
-                                        "(same lintol and stopping test as the reference's plain CG)") if args.precond
-                                else "plain CG (the reference's algorithm)",
-                                b_alg_bytes_per_update=b_alg),
-                    e2e=dict(value=dof_updates_per_step * args.steps / (ms_e2e * 1e-3), unit=UNIT,
-                             h2d_bytes_per_step=8 * n**3, d2h_bytes_per_step=8 * n**3),
+        counters = [c.cpu().numpy() for _, _, c in solve_log]
+        if args.precond:
+            alg_bytes = 8.0 * nloc * float(np.sum(6 + 11 * np.stack(counters)))
+        else:
+            alg_bytes = algorithmic_bytes(w, nloc, [c.cpu().numpy() for _, _, c in fine_log])
+            if coarse_log:
+                alg_bytes += algorithmic_bytes(w, ncoarse, [c.cpu().numpy() for _, _, c in coarse_log])
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        big = w["ndof"] * 8 * 10 > 126e6
+        cfg = dict(workload=w["name"], inputs=w["inputs"], sweeps_per_step=sweeps_per_step,
+                   parallelism=(f"{world} slabs along axis 0 (peer-memory CG)" if comm is not None else
+                                f"{world} time slices, one per GPU (PFASST, NCCL send/recv)" if pfasst and world > 1
+                                else "single GPU"),
+                   cache=(f"working set per step {'~28 GB' if w['config'] == 3 and n == 511 else '> 126 MB'} >> 126 MB L2: "
+                          "no flush needed") if big else "fields of this grid fit the 126 MB L2")
+        b_alg = None
+        if w["config"] == 4:
+            kernel = "newton_kernel (persistent Newton + inner CG)"
+            cfg.update(newton_per_solve=float(np.mean([c[0] for c in counters])),
+                       linear_per_solve=float(np.mean([c[1] for c in counters])))
+        else:
+            n_cg = float(np.mean(np.concatenate([np.atleast_1d(c) for c in counters])))
+            kernel = ("cg_pipe_kernel<3> (persistent node-batched CG, TMA-pipelined passes)" if w["config"] == 3 else
+                      "cg_pipe_kernel<2> (persistent CG, TMA-pipelined passes, one launch per node solve)")
+            C = 2 if w["problem"] == "heatNd_forced" else 1
+            base_bytes = 2 * 8 * (w["M"] * C + w["M"] + 1) / w["M"] + 32 + 16 + (8 if C == 2 else 0)
+            b_alg = base_bytes + (16 + 88 * n_cg if args.precond else 72 * n_cg)
+            cfg.update(cg_it_per_solve=n_cg, b_alg_bytes_per_update=b_alg,
+                       solver=("CG preconditioned with a degree-1 Chebyshev polynomial of the operator (same lintol and "
+                               "stopping test as the reference's plain CG)") if args.precond
+                       else "plain CG (the reference's algorithm)")
+        traffic, traffic_src = (None, None) if args.precond else measured_traffic(w, world)
+        value = updates_per_step * args.steps / (ms * 1e-3)
+        line = dict(metric=w["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True,
+                    scaling="weak" if pfasst else "strong", vs_baseline=None, dtype="f64", data="synthetic", config=cfg,
+                    e2e=dict(value=updates_per_step * args.steps / (ms_e2e * 1e-3), unit=UNIT,
+                             h2d_bytes_per_step=8 * w["ndof"], d2h_bytes_per_step=8 * w["ndof"], through=e2e_via,
+                             same_answer_as_device_leg=bool(e2e_consistent)),
                     gpu_launches=launches,
-                    roofline=dict(bound="hbm", kernel="cg_pipe_kernel<3> (persistent node-batched CG, TMA-pipelined passes)"
-                                  + (", rank 0's slab" if world > 1 else ""), achieved=achieved,
-                                  peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src, traffic=traffic,
-                                  traffic_unit="bytes per launch", traffic_source=traffic_src,
-                                  algorithmic_bytes_per_launch=alg_bytes / max(n_launch, 1),
-                                  launches=n_launch, ms_per_launch=cg_ms / max(n_launch, 1),
-                                  share_of_step=cg_ms / ms,
-                                  whole_step_achieved=b_alg * dof_updates_per_step * args.steps / (ms * 1e-3) / 1e9),
+                    roofline=dict(bound="hbm", kernel=kernel + (", rank 0's share" if world > 1 else ""),
+                                  achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, peak_source=peak_src,
+                                  traffic=traffic, traffic_unit="bytes per launch", traffic_source=traffic_src,
+                                  algorithmic_bytes_per_launch=alg_bytes / max(n_launch, 1), launches=n_launch,
+                                  ms_per_launch=k_ms / max(n_launch, 1), share_of_step=k_ms / ms),
                     other_kernels={k: dict(v, frac_of_peak=v["achieved_gbs"] / peak) for k, v in other.items()},
                     clocks=clocks)
+        if b_alg is not None:
+            line["roofline"]["whole_step_achieved"] = b_alg * updates_per_step * args.steps / (ms * 1e-3) / 1e9
+        line["check"] = check_answer(w, world, residuals, niter, uend_maxabs, write=args.write_record)
+        if line["check"]["status"] == "MISMATCH" or not e2e_consistent:
+            rc = 3
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_rate(args.ref_n, K_SWEEPS)
-            line["cpu_baseline"] = dict(
-                value=r["rate"], unit=UNIT, cores=1, kind="port",
-                sample=(f"oracle port of the reference path (scipy sparse matvec + scipy cg, single-threaded) on this "
-                        f"host, same description at {r['n']}^3, 1 step of {K_SWEEPS} sweeps in {r['seconds']:.1f} s, "
-                        f"{r['cg_per_solve']:.1f} CG it/solve; host has {os.cpu_count()} cores"))
+            try:
+                line["cpu_baseline"] = cpu_baseline(w, args.cpu_budget)
+            except Exception as e:  # no copy of the reference on this box: say so instead of substituting something else
+                line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=1, kind="reference", sample=f"unavailable: {e}")
         print(json.dumps(line))
     if world > 1:
+        flag = torch.tensor([rc], device="cuda")
+        dist.broadcast(flag, src=0)
+        rc = int(flag.item())
         dist.destroy_process_group()
+    sys.exit(rc)
 
 
 def main():
@@ -348,10 +641,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=511, help="grid points per dimension (headline: 511)")
-    ap.add_argument("--ref-n", type=int, default=127, help="grid size of the bounded CPU sample (127^3: ~15 s per step)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5], help="BASELINE.json config (headline: 3)")
+    ap.add_argument("--n", type=int, default=None, help="grid points per dimension (default: the BASELINE size)")
+    ap.add_argument("--ref-n", type=int, default=None, help="grid size of the reference arm's sample (default: auto)")
+    ap.add_argument("--ref-budget", type=float, default=300.0, help="seconds the reference arm may take in total")
+    ap.add_argument("--cpu-budget", type=float, default=100.0, help="seconds for the cpu_baseline sample of the default arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-controller", action="store_true",
+                    help="e2e leg through the stand-alone controller even when oracle/_ref is present")
     ap.add_argument("--precond", action="store_true", help="node solves with the polynomial preconditioner")
+    ap.add_argument("--write-record", action="store_true", help="(re)write the committed answer record of this workload")
     args = ap.parse_args()
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) == 0:

@@ -58,10 +58,13 @@ def main():
         niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
         work = {k[len("work_"):]: [int(v) for _, v in get_sorted(stats, type=k, sortby="time")]
                 for k in sorted({e.type for e in stats if str(e.type).startswith("work_")})}
+        times = [t for t, _ in get_sorted(stats, type="niter", sortby="time")]
+        hist = [[float(v) for _, v in get_sorted(stats, time=t, type="residual_post_iteration", sortby="iter")][-6:]
+                for t in times]
         N, M = int(np.prod(P.nvars)), L.sweep.coll.num_nodes
         print(json.dumps(dict(config=name, steps=args.steps, niter=niter, work=work, wall_s=wall,
                               ms_per_step=1e3 * wall / args.steps, dof_node_updates_per_s=N * M * sum(niter) / wall,
-                              uend_maxnorm=float(abs(uend)))), flush=True)
+                              uend_maxnorm=float(abs(uend)), last_residuals=hist)), flush=True)
 
 
 if __name__ == "__main__":
