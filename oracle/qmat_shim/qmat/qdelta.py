@@ -4,6 +4,8 @@ Call sites: ``pySDC/core/sweeper.py:97-123`` (``QDELTA_GENERATORS[name](qGen=col
 ``genCoeffs(k=k)``, ``genCoeffs(k=k, dTau=True) -> (QDelta, dTau)``) and ``:262-276``
 (``isKDependent()``, ``type(gen).__name__`` used again as a key of ``QDELTA_GENERATORS``).
 """
+import warnings
+
 import numpy as np
 import scipy.linalg as spl
 
@@ -88,7 +90,61 @@ class MIN_SR_NS(QDeltaGenerator):
         return np.diag(self.nodes - self.tLeft) / self.M
 
 
-class MIN_SR_FLEX(QDeltaGenerator):
+class MIN_SR_S(QDeltaGenerator):
+    """Diagonal QDelta with minimal spectral radius of the stiff-limit iteration matrix I - QDelta^-1 Q (published
+    algorithm of qmat / pySDC <= 5.4 ``get_Qdelta_implicit('MIN-SR-S')``): the coefficients d solve the nilpotency
+    conditions  det((1 - z) I + z diag(1/d) Q) = 1  at z = the nodes; the nonlinear solve is started from a power law
+    a * nodes**b / M fitted incrementally to the solutions for fewer nodes."""
+
+    def __init__(self, qGen=None, tLeft=0.0, Q=None, nodes=None, nodeType="LEGENDRE", quadType="RADAU-RIGHT", **kw):
+        super().__init__(qGen=qGen, tLeft=tLeft, Q=Q, nodes=nodes, **kw)
+        self.nodeType = getattr(qGen, "nodeType", nodeType)
+        self.quadType = getattr(qGen, "quadType", quadType)
+
+    def _coeffs_for(self, M, a, b):
+        from scipy import optimize
+
+        from .qcoeff.collocation import Collocation
+
+        coll = Collocation(nNodes=M, nodeType=self.nodeType, quadType=self.quadType, tLeft=0.0, tRight=1.0)
+        QM, nodesM = coll.Q, coll.nodes
+        first_is_zero = self.quadType in ("LOBATTO", "RADAU-LEFT")
+        if first_is_zero:
+            QM, nodesM = QM[1:, 1:], nodesM[1:]
+        nC = nodesM.size
+        if nC == 1:
+            coeffs = np.diag(QM).copy()
+        else:
+            def nilpotency(c):
+                return np.array([np.linalg.det((1 - z) * np.eye(nC) + z * np.diag(1 / np.asarray(c)) @ QM) - 1
+                                 for z in nodesM])
+
+            c0 = nodesM / M if a is None else a * nodesM**b / M
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)  # 'xtol too small': converged to round-off
+                coeffs = optimize.fsolve(nilpotency, c0, xtol=1e-15)
+        if first_is_zero:
+            coeffs, nodesM = np.concatenate(([0.0], coeffs)), np.concatenate(([0.0], nodesM))
+        return coeffs, nodesM
+
+    def computeQDelta(self, k=None):
+        from scipy import optimize
+
+        a = b = None
+        m0 = 2 if self.quadType in ("LOBATTO", "RADAU-LEFT") else 1
+        coeffs = None
+        for m in range(m0, self.M + 1):
+            coeffs, nodes = self._coeffs_for(m, a, b)
+            if m > 1:
+                target = coeffs * m
+                a, b = optimize.minimize(lambda ab: np.linalg.norm(ab[0] * nodes**ab[1] - target), [1.0, 1.0],
+                                         method="nelder-mead").x
+        # coefficients are computed on [0, 1]; scale to the step the generator was built for
+        scale = (self.nodes[-1] - self.tLeft) / 1.0 if self.quadType in ("LOBATTO", "RADAU-RIGHT") else 1.0
+        return np.diag(coeffs) * scale
+
+
+class MIN_SR_FLEX(MIN_SR_S):
     def isKDependent(self):
         return True
 
@@ -96,14 +152,15 @@ class MIN_SR_FLEX(QDeltaGenerator):
         k = 1 if k is None else int(k)
         if k < 1:
             k = 1
-        if k > self.M:
-            raise NotImplementedError("MIN-SR-FLEX falls back to MIN-SR-S for k > M; not restated in the stand-in")
+        if k > self.M:  # beyond M sweeps the flexible scheme continues with the stiff-limit coefficients
+            return super().computeQDelta()
         return np.diag(self.nodes - self.tLeft) / k
 
 
 # the reference looks generators up by alias AND by class name (sweeper.py:273,275)
 MIN_SR_NS.__name__ = "MIN-SR-NS"
 MIN_SR_FLEX.__name__ = "MIN-SR-FLEX"
+MIN_SR_S.__name__ = "MIN-SR-S"
 
 QDELTA_GENERATORS = {
     "BE": BE, "IE": BE,
@@ -114,5 +171,6 @@ QDELTA_GENERATORS = {
     "BEPAR": BEPAR, "IEpar": BEPAR,
     "Jacobi": Jacobi, "Qpar": Jacobi,
     "MIN-SR-NS": MIN_SR_NS,
+    "MIN-SR-S": MIN_SR_S,
     "MIN-SR-FLEX": MIN_SR_FLEX,
 }

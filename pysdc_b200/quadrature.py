@@ -9,6 +9,8 @@ Written independently of the test oracle's qmat stand-in (different algorithms: 
 quadrature); ``tests/test_quadrature.py`` checks that the two agree to round-off and re-asserts the reference's
 property tests (``pySDC/tests/test_collocation.py``, ``tests/test_sweepers/test_preconditioners.py``).
 """
+import warnings
+
 import numpy as np
 import scipy.linalg
 import scipy.special
@@ -166,13 +168,57 @@ class _MinSrNs(QDeltaGenerator):
         return np.diag(self.nodes - self.tleft) / self.M
 
 
-class _MinSrFlex(QDeltaGenerator):
+def _min_sr_s_diagonal(M, node_type, quad_type):
+    """Diagonal d (on [0, 1]) making the stiff-limit iteration matrix K = I - diag(d)^-1 Q nilpotent, i.e. all
+    coefficients of det(lambda I - K) but the leading one vanish.  Equivalent published form (qmat ``MIN-SR-S``):
+    det((1 - z) I + z diag(1/d) Q) = 1 at M distinct z (the nodes).  The root near the power law a * nodes**b / M is
+    taken, found incrementally in M as the published algorithm does, so that the same branch is selected."""
+    import scipy.optimize
+
+    first_is_zero = quad_type in ("LOBATTO", "RADAU-LEFT")
+    a = b = None
+    d = None
+    for m in range(2 if first_is_zero else 1, M + 1):
+        c = CollBase(num_nodes=m, tleft=0.0, tright=1.0, node_type=node_type, quad_type=quad_type)
+        Q, t = c.Qmat[1:, 1:], c.nodes
+        if first_is_zero:
+            Q, t = Q[1:, 1:], t[1:]
+        k = t.size
+        if k == 1:
+            d = np.array([Q[0, 0]])
+        else:
+            eye = np.eye(k)
+
+            def conditions(x):
+                G = Q / np.asarray(x)[:, None]  # diag(1/x) Q
+                return np.array([np.linalg.det((1.0 - z) * eye + z * G) - 1.0 for z in t])
+
+            start = t / m if a is None else a * t**b / m
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", RuntimeWarning)  # 'xtol too small': converged to round-off
+                d = scipy.optimize.fsolve(conditions, start, xtol=1e-15)
+        if m > 1:
+            target = d * m
+            a, b = scipy.optimize.minimize(lambda ab: np.linalg.norm(ab[0] * t**ab[1] - target), [1.0, 1.0],
+                                           method="nelder-mead").x
+    return np.concatenate(([0.0], d)) if first_is_zero else d
+
+
+class _MinSrS(QDeltaGenerator):
+    """MIN-SR-S: diagonal, minimal spectral radius of the sweep's iteration matrix in the stiff limit."""
+
+    def coeffs(self, k=None):
+        d = _min_sr_s_diagonal(self.M, self.coll.node_type, self.coll.quad_type)
+        return np.diag(d) * (self.coll.tright - self.coll.tleft)
+
+
+class _MinSrFlex(_MinSrS):
     k_dependent = True
 
     def coeffs(self, k=None):
         k = 1 if k is None or k < 1 else int(k)
-        if k > self.M:
-            raise ParameterError("MIN-SR-FLEX is defined for sweeps k <= num_nodes (run it with nsweeps = num_nodes)")
+        if k > self.M:  # qmat: beyond M sweeps MIN-SR-FLEX continues with the MIN-SR-S coefficients
+            return super().coeffs()
         return np.diag(self.nodes - self.tleft) / k
 
 
@@ -184,6 +230,7 @@ QDELTA_GENERATORS = {
     "IEpar": _IEpar, "BEPAR": _IEpar,
     "Qpar": _Qpar, "Jacobi": _Qpar,
     "MIN-SR-NS": _MinSrNs,
+    "MIN-SR-S": _MinSrS,
     "MIN-SR-FLEX": _MinSrFlex,
 }
 

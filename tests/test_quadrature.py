@@ -49,7 +49,7 @@ def test_polynomial_exactness_and_S(M, quad):
         np.testing.assert_allclose(c.delta_m.sum(), c.nodes[-1] - a, atol=1e-15)
 
 
-@pytest.mark.parametrize("name", ["IE", "EE", "LU", "PIC", "IEpar", "Qpar", "MIN-SR-NS", "MIN-SR-FLEX"])
+@pytest.mark.parametrize("name", ["IE", "EE", "LU", "PIC", "IEpar", "Qpar", "MIN-SR-NS", "MIN-SR-S", "MIN-SR-FLEX"])
 @pytest.mark.parametrize("M", [2, 3, 4, 5])
 def test_qdelta_against_oracle_shim(M, name):
     from qmat import Q_GENERATORS
@@ -59,9 +59,10 @@ def test_qdelta_against_oracle_shim(M, name):
     g = Q_GENERATORS["Collocation"](nNodes=M, nodeType="LEGENDRE", quadType="RADAU-RIGHT", tLeft=0, tRight=1)
     mine, ref = make_qdelta_generator(name, c), QDELTA_GENERATORS[name](qGen=g, tLeft=0)
     assert mine.isKDependent() == ref.isKDependent()
-    for k in ([None] if not mine.isKDependent() else [1, 2, M]):
+    # k > M: MIN-SR-FLEX continues with the MIN-SR-S coefficients (a nonlinear solve: agreement to solver accuracy)
+    for k in ([None] if not mine.isKDependent() else [1, 2, M, M + 1]):
         QD, dtau = ref.genCoeffs(k=k, dTau=True)
-        np.testing.assert_allclose(mine.coeffs(k), QD, rtol=0, atol=2e-15)
+        np.testing.assert_allclose(mine.coeffs(k), QD, rtol=0, atol=1e-12 if name == "MIN-SR-S" or (k or 0) > M else 2e-15)
         np.testing.assert_allclose(mine.dtau(k), dtau, rtol=0, atol=2e-15)
 
 
@@ -79,6 +80,10 @@ def test_preconditioner_properties(M):
     QD = make_qdelta_generator("MIN-SR-NS", c).coeffs()
     assert np.allclose(np.diag(np.diag(QD)), QD)
     assert np.max(np.abs(np.linalg.eigvals(Q - QD))) < 1e-7 ** (1.0 / M) * 10  # non-stiff limit: spectral radius ~ 0
+    # MIN-SR-S (test_preconditioners.py:15-41): diagonal, stiff-limit iteration matrix nilpotent
+    QD = make_qdelta_generator("MIN-SR-S", c).coeffs()
+    assert np.allclose(np.diag(np.diag(QD)), QD) and np.all(np.diag(QD) > 0)
+    assert np.max(np.abs(np.linalg.eigvals(I - np.linalg.solve(QD, Q)))) < 2e-2 ** (1.0 if M > 4 else 2.0)
     flex = make_qdelta_generator("MIN-SR-FLEX", c)
     prod = I
     for k in range(1, M + 1):
