@@ -172,13 +172,17 @@ int sdcb200_heat_direct_solve_1d(int n, int bc, int B, const double* m_diag_host
                                  const double* const* rhs, double* const* x, void* stream);
 
 /* ---- K4: Allen-Cahn Newton ------------------------------------------------------------------------------------------
- * Newton iteration with inner CG on the Jacobian, whole solve in one persistent launch
- * (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205).  u: in = initial guess, out = solution.
- * counters_dev[0] += Newton iterations, counters_dev[1] += CG iterations.  inexact_ratio <= 0 disables :176-177.   */
-size_t sdcb200_newton_workspace_bytes(int n);
-int sdcb200_allencahn_newton_solve(int n, double factor, double a_diag, double a_off, double inv_eps2, int nu_exp,
-                                   const double* rhs, double* u, double newton_tol, int newton_maxiter,
-                                   double lin_tol, int lin_maxiter, double inexact_ratio,
+ * Newton iteration with inner CG on the Jacobian for B node systems  u_b - factor_b (A u_b + 1/eps^2 u_b (1 - u_b^nu)) =
+ * rhs_b, whole solve in one persistent launch (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205; B > 1:
+ * the independent node systems of a diagonal QDelta).  u[b]: in = initial guess, out = solution.  Systems leave the
+ * Newton loop and the inner CG individually.  counters_dev[0] += Newton iterations, counters_dev[1] += CG iterations
+ * (summed over the systems).  inexact_ratio <= 0 disables :176-177.  The inner CG runs the TMA-pipelined passes with
+ * periodic wrap boxes and the Jacobian diagonal as a tile-only box.  work: sdcb200_newton_workspace_bytes(n, B) bytes,
+ * 256-byte aligned, zero-filled before its first use.                                                               */
+size_t sdcb200_newton_workspace_bytes(int n, int B);
+int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, double a_diag, double a_off, double inv_eps2,
+                                   int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
+                                   int newton_maxiter, double lin_tol, int lin_maxiter, double inexact_ratio,
                                    void* work, size_t work_bytes, int* counters_dev, void* stream);
 
 #ifdef __cplusplus

@@ -99,10 +99,17 @@ def collect():
         with open(path) as f:
             r = json.load(f)
         out.setdefault(r["config"], []).append(r)
+    golden = {"config2": "run_config2_heat2d_imex_lu_2047", "config5": "pfasst_config5_1023_p8"}
     for cfg, runs in out.items():
-        dst = os.path.join(os.path.dirname(HERE), "tests", "golden", f"sensitivity_{cfg}.json")
+        gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
+        base = np.load(os.path.join(gdir, golden[cfg] + ".npz"))["niter"].tolist()  # the unperturbed reference run
+        for r in runs:
+            r["niter_unperturbed"] = base
+            r["residuals"] = [h[-4:] for h in r["residuals"]]  # the last iterations: where the stopping test is decided
+        dst = os.path.join(gdir, f"sensitivity_{cfg}.json")
         with open(dst, "w") as f:
-            json.dump(dict(note="unmodified reference with rounding-level input perturbations (oracle/sensitivity.py)",
+            json.dump(dict(note="unmodified reference with rounding-level input perturbations (oracle/sensitivity.py); "
+                                "niter_unperturbed = the reference's own answer on the unperturbed inputs",
                            runs=runs), f, indent=1)
         print("wrote", dst, [(r["perturbation"], r["niter"]) for r in runs])
 

@@ -54,8 +54,8 @@ def _declare(lib):
         "sdcb200_heat_eval_f_slab": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_axis_apply": (c_int, [c_ll, c_int, c_ll, c_int, _c_dp, _c_dp, _c_dp, c_ll, c_ll, _c_dp, c_ll, c_ll, _c_dp]),
         "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
-        "sdcb200_newton_workspace_bytes": (c_sz, [c_int]),
-        "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_d, c_d, c_d, c_d, c_int, _c_dp, _c_dp, c_d, c_int, c_d,
+        "sdcb200_newton_workspace_bytes": (c_sz, [c_int, c_int]),
+        "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
                                                    c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
     }
     for name, (res, args) in sig.items():
@@ -244,15 +244,16 @@ class CudaBackend:
         self._check(self.lib.sdcb200_heat_direct_solve_1d(lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off),
                                                           _ptr_array(rhs), _ptr_array(xs), self._stream()))
 
-    def newton_workspace(self, lay):
-        nbytes = self.lib.sdcb200_newton_workspace_bytes(lay.n)
+    def newton_workspace(self, lay, B):
+        nbytes = self.lib.sdcb200_newton_workspace_bytes(lay.n, B)
         return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
 
-    def allencahn_newton_solve(self, lay, factor, a_diag, a_off, inv_eps2, nu_exp, rhs, u, newton_tol, newton_maxiter,
+    def allencahn_newton_solve(self, lay, factors, a_diag, a_off, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter,
                                lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
+        """Newton + inner CG for the len(us) systems (rhs[b], factors[b]) in ONE persistent launch, in place on us[b]."""
         self.launches += 1
         self._check(self.lib.sdcb200_allencahn_newton_solve(
-            lay.n, float(factor), a_diag, a_off, inv_eps2, int(nu_exp), rhs.data_ptr(), u.data_ptr(),
+            lay.n, len(us), _dbl_array(factors), a_diag, a_off, inv_eps2, int(nu_exp), _ptr_array(rhs), _ptr_array(us),
             float(newton_tol), int(newton_maxiter), float(lin_tol), int(lin_maxiter),
             float(inexact_ratio or 0.0), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(), self._stream()))
 

@@ -9,6 +9,7 @@
 // scheduled as two fused passes per iteration (see cg_collective).
 #include "cg_common.cuh"
 #include "cg_pipe.cuh"
+#include "pipe_host.cuh"
 
 namespace sdcb200 {
 namespace {
@@ -201,31 +202,38 @@ __device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgSh
     else __syncthreads();
 }
 
-template <int NDIM, bool SLAB>
-__device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const PipeMaps& maps, double rtol, int maxiter,
-                                   double* partials, unsigned* bar, CgShared& sh, PipeSmem& sm, const SlabLink* link) {
+// All threads of the grid (and, on slabs, of all ranks) call this with identical arguments.  `start_mask`: the systems
+// that take part (bit b); the others are left untouched.  sh.rtol[b] holds each system's relative tolerance.
+template <int NDIM, bool SLAB, bool PER, bool DIAG, class SMEM>
+__device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, const Sys* s, const PipeMaps& maps,
+                                   int maxiter, double* partials, unsigned* bar, CgShared& sh, SMEM& sm,
+                                   const SlabLink* link, unsigned& kstep) {
     const Units U = make_units(g, (int)gridDim.x);
     const PUnits PU = make_punits(g, 1, (int)gridDim.x);
     const long long n2 = g.owned / 2;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long gstride = (long long)gridDim.x * blockDim.x;
-    unsigned kstep = 0;
+    PipeCtl& ctl = sm.ctl;
     unsigned long long seq = SLAB ? *link->seq : 0ull;
     __shared__ int r_slots[kMailVals], r_sys[kMailVals];
+    __shared__ int r_count;
 
     // ---- r = b - M x0, ||b||^2, ||r||^2 ------------------------------------------------------------------------------
     for (int b = 0; b < B; ++b) {
+        if (!(start_mask >> b & 1u)) continue;
         const Sys& S = s[b];
         double bb = 0.0, rr = 0.0;
         if (threadIdx.x < kThreads) {
             double* r_lo = SLAB && link->has_lo ? link->lo_r_halo[b] : nullptr;
             double* r_hi = SLAB && link->has_hi ? link->hi_r_halo[b] : nullptr;
             for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
-                stencil_unit<NDIM, false>(g, U, S.x, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
+                stencil_unit<NDIM, PER>(g, U, S.x, unit, [&](long long idx, double2 c, double2 nb, bool v0, bool v1) {
                     const double2 rhs = ld2(S.b + idx);
+                    double2 d = make_double2(S.m_diag, S.m_diag);
+                    if (DIAG) d = ld2(S.dvec + idx);
                     double2 r;
-                    r.x = v0 ? rhs.x - fma(S.m_off, nb.x, S.m_diag * c.x) : 0.0;
-                    r.y = v1 ? rhs.y - fma(S.m_off, nb.y, S.m_diag * c.y) : 0.0;
+                    r.x = v0 ? rhs.x - fma(S.m_off, nb.x, d.x * c.x) : 0.0;
+                    r.y = v1 ? rhs.y - fma(S.m_off, nb.y, d.y * c.y) : 0.0;
                     st2(S.r + idx, r);
                     if (SLAB) {
                         if (r_lo != nullptr && idx < g.sz) st2(r_lo + idx, r);
@@ -244,20 +252,25 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
         put_partial(partials, kSlotSetup1, b, rr);
     }
     if (threadIdx.x == 0) {
+        int nv = 0;
         for (int b = 0; b < B; ++b) {
-            r_slots[2 * b] = kSlotSetup0;
-            r_sys[2 * b] = b;
-            r_slots[2 * b + 1] = kSlotSetup1;
-            r_sys[2 * b + 1] = b;
+            if (!(start_mask >> b & 1u)) continue;
+            r_slots[nv] = kSlotSetup0;
+            r_sys[nv++] = b;
+            r_slots[nv] = kSlotSetup1;
+            r_sys[nv++] = b;
         }
+        r_count = nv;
     }
+    __syncthreads();
     fence_proxy_async_global();
-    reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, 2 * B);
+    reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, r_count);
     if (threadIdx.x == 0) {
         unsigned act = 0;
-        for (int b = 0; b < B; ++b) {
-            sh.bb[b] = sh.glob[2 * b];
-            sh.rr[b] = sh.glob[2 * b + 1];
+        for (int i = 0; i < r_count; i += 2) {
+            const int b = r_sys[i];
+            sh.bb[b] = sh.glob[i];
+            sh.rr[b] = sh.glob[i + 1];
             sh.iters[b] = 0;
             sh.rho_prev[b] = 1.0;
             if (sh.bb[b] != 0.0) act |= 1u << b;  // scipy: ||b|| == 0 -> return b
@@ -266,11 +279,13 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
     }
     __syncthreads();
     for (int b = 0; b < B; ++b) {
-        if (sh.bb[b] == 0.0) {
+        if ((start_mask >> b & 1u) && sh.bb[b] == 0.0) {
             for (long long i = gtid; i < n2; i += gstride) st2(s[b].x + 2 * i, make_double2(0.0, 0.0));
         }
     }
 
+    PassArgs pa;
+    pa.link = link;
     // preconditioned runs: z = C(M) r for the systems that will iterate, r.z
     const bool pc = s[0].z != nullptr;
     if (pc) {
@@ -278,18 +293,19 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
             int na = 0;
             for (int b = 0; b < B; ++b)
                 if (sh.active >> b & 1u) {
-                    sm.act_list[na] = b;
+                    ctl.act_list[na] = b;
                     r_sys[na] = b;
                     r_slots[na] = kSlotC;
                     ++na;
                 }
-            sm.nact = na;
+            ctl.nact = na;
         }
         __syncthreads();
-        if (sm.nact > 0) {
-            const int nc = sm.nact;
+        if (ctl.nact > 0) {
+            const int nc = ctl.nact;
             fence_proxy_async_global();
-            pipe_phase_c<NDIM>(g, PU, s, maps, sm, partials, kstep, link);
+            pa.slot = kSlotC;
+            pipe_pass<NDIM, PER, DIAG, kPhaseC>(g, PU, s, maps, sh, sm, partials, kstep, pa);
             fence_proxy_async_global();
             reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc);
             if ((int)threadIdx.x < nc) sh.rz[r_sys[threadIdx.x]] = sh.glob[threadIdx.x];
@@ -306,28 +322,30 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
             int na = 0;
             for (int b = 0; b < B; ++b) {
                 if (!(act >> b & 1u)) continue;
-                const double atol = rtol * sqrt(sh.bb[b]);
+                const double atol = sh.rtol[b] * sqrt(sh.bb[b]);
                 if (sqrt(sh.rr[b]) < atol || it >= maxiter) {
                     act &= ~(1u << b);
                 } else {
                     sh.beta[b] = it > 0 ? sh.rz[b] / sh.rho_prev[b] : 0.0;
-                    sm.act_list[na] = b;
+                    ctl.act_list[na] = b;
                     r_sys[na] = b;
                     ++na;
                 }
             }
             sh.active = act;
-            sm.nact = na;
+            ctl.nact = na;
         }
         __syncthreads();
         const unsigned act = sh.active;
         if (act == 0) break;
-        const int nact = sm.nact;
-        const int cur = it & 1;  // p_new goes to (cur ? S.q : S.p), p_old is the other buffer
+        const int nact = ctl.nact;
+        pa.cur = it & 1;  // p_new goes to (cur ? S.q : S.p), p_old is the other buffer
+        pa.first = it == 0;
 
         // ---- phase A ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
-        pipe_phase_a<NDIM>(g, PU, s, maps, it == 0, cur, sh, sm, partials, kstep);
+        pa.slot = kSlotA;
+        pipe_pass<NDIM, PER, DIAG, kPhaseA>(g, PU, s, maps, sh, sm, partials, kstep, pa);
         if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotA;
         fence_proxy_async_global();
         reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
@@ -336,7 +354,8 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
 
         // ---- phase B ---------------------------------------------------------------------------------------------------
         fence_proxy_async_global();
-        pipe_phase_b<NDIM>(g, PU, s, maps, cur, sh, sm, partials, kstep, link);
+        pa.slot = kSlotB;
+        pipe_pass<NDIM, PER, DIAG, kPhaseB>(g, PU, s, maps, sh, sm, partials, kstep, pa);
         if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotB;
         fence_proxy_async_global();
         reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
@@ -357,20 +376,21 @@ __device__ void cg_collective_pipe(const Geom& g, int B, const Sys* s, const Pip
                 int na = 0;
                 for (int b = 0; b < B; ++b) {
                     if (!(act >> b & 1u)) continue;
-                    if (sqrt(sh.rr[b]) < rtol * sqrt(sh.bb[b]) || it + 1 >= maxiter) continue;
-                    sm.act_list[na] = b;
+                    if (sqrt(sh.rr[b]) < sh.rtol[b] * sqrt(sh.bb[b]) || it + 1 >= maxiter) continue;
+                    ctl.act_list[na] = b;
                     r_sys[na] = b;
                     r_slots[na] = kSlotC;
                     ++na;
                 }
-                sm.nact = na;
+                ctl.nact = na;
             }
             __syncthreads();
-            const int nc = sm.nact;
+            const int nc = ctl.nact;
             __syncthreads();  // everybody holds nc before thread 0 may rewrite the list at the top of the loop
             if (nc > 0) {
                 fence_proxy_async_global();
-                pipe_phase_c<NDIM>(g, PU, s, maps, sm, partials, kstep, link);
+                pa.slot = kSlotC;
+                pipe_pass<NDIM, PER, DIAG, kPhaseC>(g, PU, s, maps, sh, sm, partials, kstep, pa);
                 fence_proxy_async_global();
                 reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc);
                 if ((int)threadIdx.x < nc) {
@@ -391,15 +411,19 @@ struct PipeArgs {
     SlabLink link;  // used by the SLAB instantiation only
 };
 
-template <int NDIM, bool SLAB>
+template <int NDIM, bool SLAB, bool PER>
 __global__ void __maxnreg__(112) cg_pipe_kernel(const __grid_constant__ PipeArgs pa) {
+    using Smem = PipeSmemT<PER, false>;
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
-    PipeSmem& sm = *reinterpret_cast<PipeSmem*>(pipe_smem_raw);
+    Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
     __shared__ CgShared sh;
     const CgArgs& a = pa.cg;
-    pipe_smem_init(sm);
-    cg_collective_pipe<NDIM, SLAB>(a.g, a.B, a.s, pa.maps, a.rtol, a.maxiter, a.partials, a.bar, sh, sm,
-                                   SLAB ? &pa.link : nullptr);
+    pipe_ctl_init(sm.ctl, PipeCfg<PER, false>::kStages);
+    if (threadIdx.x < SDCB200_MAX_NODES) sh.rtol[threadIdx.x] = a.rtol;
+    __syncthreads();
+    unsigned kstep = 0;
+    cg_collective_pipe<NDIM, SLAB, PER, false>(a.g, a.B, (1u << a.B) - 1u, a.s, pa.maps, a.maxiter, a.partials, a.bar, sh,
+                                                sm, SLAB ? &pa.link : nullptr, kstep);
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.iters_out != nullptr)
         for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
 }
@@ -412,88 +436,130 @@ __device__ __forceinline__ double ipow(double u, int k) {
     return r;
 }
 
-__global__ void __launch_bounds__(kThreads) newton_kernel(const __grid_constant__ NewtonArgs a) {
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: Allen-Cahn Newton (AllenCahn_2D_FD.py:137-205) for B node systems in one persistent launch.  Every Newton
+// iteration evaluates the nonlinear residual g_b and the Jacobian diagonal d_b of the systems that are still iterating
+// (register-marching pass: one of ~200 passes of a Newton step), then runs the pipelined CG on  (d_b I - factor_b a_off
+// S) z_b = g_b  for those systems together - periodic wrap sets, diagonal as a tile-only box - and updates u_b -= z_b.
+// Systems drop out of the Newton loop individually (residual below newton_tol or iteration budget spent), systems drop
+// out of the inner CG individually; counters are per system, so a batched solve counts what separate solves count.
+// ---------------------------------------------------------------------------------------------------------------------
+struct NewtonPipeArgs {
+    NewtonArgs nw;
+    PipeMaps maps;
+};
+
+__global__ void __maxnreg__(112) newton_pipe_kernel(const __grid_constant__ NewtonPipeArgs npa) {
+    using Smem = PipeSmemT<true, true>;
+    extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
     __shared__ CgShared sh;
-    __shared__ Sys sys;
-    __shared__ int s_newton, s_linear;
-    const Geom& g = a.g;
+    __shared__ int s_newton[SDCB200_MAX_NODES], s_linear[SDCB200_MAX_NODES];
+    __shared__ unsigned s_active;
+    const NewtonArgs& a = npa.nw;
+    const CgArgs& cg = a.cg;
+    const Geom& g = cg.g;
+    const int B = cg.B;
     const Units U = make_units(g);
     const long long n2 = g.vol / 2;
-    const long long gtid = (long long)blockIdx.x * kThreads + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * kThreads;
-    if (threadIdx.x == 0) {
-        s_newton = 0;
-        s_linear = 0;
-        sys.b = a.gvec;
-        sys.x = a.z;
-        sys.r = a.r;
-        sys.p = a.p;
-        sys.q = a.q;
-        sys.dvec = a.dvec;
-        sys.m_diag = 0.0;
-        sys.m_off = -(a.factor * a.a_off);
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    pipe_ctl_init(sm.ctl, PipeCfg<true, true>::kStages);
+    if (threadIdx.x < SDCB200_MAX_NODES) {
+        s_newton[threadIdx.x] = 0;
+        s_linear[threadIdx.x] = 0;
+        sh.rtol[threadIdx.x] = a.lin_tol;
     }
+    if (threadIdx.x == 0) s_active = (1u << B) - 1u;
     __syncthreads();
-    double lin_tol = a.lin_tol;
-    int n = 0;
-    while (n < a.newton_maxiter) {
+    unsigned kstep = 0;
+    for (;;) {
+        const unsigned act = s_active;
         // g = u - factor*(A u + 1/eps^2 u (1 - u^nu)) - rhs ;  Jacobian diagonal ;  z = 0  (AllenCahn_2D_FD.py:170,183)
-        double gmax = 0.0;
-        for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
-            stencil_unit<2, true>(g, U, a.u, unit, [&](long long idx, double2 c, double2 nb, bool, bool) {
-                const double2 rhs = ld2(a.rhs + idx);
-                double2 gv, dv;
-                {
-                    const double Au = fma(a.a_off, nb.x, a.a_diag * c.x);
-                    const double un = ipow(c.x, a.nu_exp);
-                    const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.x), __dsub_rn(1.0, un));
-                    gv.x = __dsub_rn(__dsub_rn(c.x, __dmul_rn(a.factor, __dadd_rn(Au, react))), rhs.x);
-                    const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
-                    dv.x = __dsub_rn(1.0, __dmul_rn(a.factor, __dadd_rn(a.a_diag, jr)));
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const NewtonSys& N = a.ns[b];
+            const Sys& S = cg.s[b];
+            double* dvec = const_cast<double*>(S.dvec);
+            double* gvec = const_cast<double*>(S.b);
+            const double factor = N.factor;
+            double gmax = 0.0;
+            if (threadIdx.x < kThreads) {
+                for (int unit = blockIdx.x; unit < U.per_field; unit += gridDim.x) {
+                    stencil_unit<2, true>(g, U, N.u, unit, [&](long long idx, double2 c, double2 nb, bool, bool) {
+                        const double2 rhs = ld2(N.rhs + idx);
+                        double2 gv, dv;
+                        {
+                            const double Au = fma(a.a_off, nb.x, a.a_diag * c.x);
+                            const double un = ipow(c.x, a.nu_exp);
+                            const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.x), __dsub_rn(1.0, un));
+                            gv.x = __dsub_rn(__dsub_rn(c.x, __dmul_rn(factor, __dadd_rn(Au, react))), rhs.x);
+                            const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
+                            dv.x = __dsub_rn(1.0, __dmul_rn(factor, __dadd_rn(a.a_diag, jr)));
+                        }
+                        {
+                            const double Au = fma(a.a_off, nb.y, a.a_diag * c.y);
+                            const double un = ipow(c.y, a.nu_exp);
+                            const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.y), __dsub_rn(1.0, un));
+                            gv.y = __dsub_rn(__dsub_rn(c.y, __dmul_rn(factor, __dadd_rn(Au, react))), rhs.y);
+                            const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
+                            dv.y = __dsub_rn(1.0, __dmul_rn(factor, __dadd_rn(a.a_diag, jr)));
+                        }
+                        st2(gvec + idx, gv);
+                        st2(dvec + idx, dv);
+                        st2(S.x + idx, make_double2(0.0, 0.0));
+                        gmax = fmax(gmax, fmax(fabs(gv.x), fabs(gv.y)));
+                        if (gv.x != gv.x || gv.y != gv.y) gmax = INFINITY;  // NaN: never "converged"
+                    });
                 }
-                {
-                    const double Au = fma(a.a_off, nb.y, a.a_diag * c.y);
-                    const double un = ipow(c.y, a.nu_exp);
-                    const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.y), __dsub_rn(1.0, un));
-                    gv.y = __dsub_rn(__dsub_rn(c.y, __dmul_rn(a.factor, __dadd_rn(Au, react))), rhs.y);
-                    const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
-                    dv.y = __dsub_rn(1.0, __dmul_rn(a.factor, __dadd_rn(a.a_diag, jr)));
-                }
-                st2(a.gvec + idx, gv);
-                st2(a.dvec + idx, dv);
-                st2(a.z + idx, make_double2(0.0, 0.0));
-                gmax = fmax(gmax, fmax(fabs(gv.x), fabs(gv.y)));
-                if (gv.x != gv.x || gv.y != gv.y) gmax = INFINITY;  // NaN: never "converged"
-            });
+            }
+            gmax = block_max(gmax, sh.scratch);
+            put_partial(cg.partials, kSlotNewton, b, gmax);
         }
-        gmax = block_max(gmax, sh.scratch);
-        put_partial(a.partials, kSlotC, 0, gmax);
-        grid_barrier(a.bar);
-        const double res = grid_max(a.partials, kSlotC, 0, sh.scratch);
-        if (a.inexact_ratio > 0.0) lin_tol = res * a.inexact_ratio;
-        if (res < a.newton_tol) break;
-        grid_barrier(a.bar);  // everybody has read the residual norm before anybody can come back here and rewrite it
+        grid_barrier(cg.bar);
+        for (int b = 0; b < B; ++b) {
+            if (!(act >> b & 1u)) continue;
+            const double res = grid_max(cg.partials, kSlotNewton, b, sh.scratch);
+            if (threadIdx.x == 0) {
+                if (a.inexact_ratio > 0.0) sh.rtol[b] = res * a.inexact_ratio;
+                if (res < a.newton_tol || s_newton[b] >= a.newton_maxiter) s_active &= ~(1u << b);
+            }
+        }
+        __syncthreads();
+        const unsigned go = s_active;
+        if (go == 0) break;
+        grid_barrier(cg.bar);  // everybody has read the residual norms before anybody can come back and rewrite them
 
-        cg_collective<2, true>(g, 1, &sys, lin_tol, a.lin_maxiter, a.partials, a.bar, sh);
-        if (threadIdx.x == 0) {
-            s_linear += sh.iters[0];
-            s_newton += 1;
+        cg_collective_pipe<2, false, true, true>(g, B, go, cg.s, npa.maps, a.lin_maxiter, cg.partials, cg.bar, sh, sm,
+                                                 nullptr, kstep);
+        if ((int)threadIdx.x < B && (go >> threadIdx.x & 1u)) {
+            s_linear[threadIdx.x] += sh.iters[threadIdx.x];
+            s_newton[threadIdx.x] += 1;
         }
         // u -= z
-        for (long long i = gtid; i < n2; i += gstride) {
-            double2 u = ld2(a.u + 2 * i);
-            const double2 z = ld2(a.z + 2 * i);
-            u.x = __dsub_rn(u.x, z.x);
-            u.y = __dsub_rn(u.y, z.y);
-            st2(a.u + 2 * i, u);
+        for (int b = 0; b < B; ++b) {
+            if (!(go >> b & 1u)) continue;
+            double* u = a.ns[b].u;
+            const double* z = cg.s[b].x;
+            for (long long i = gtid; i < n2; i += gstride) {
+                double2 uv = ld2(u + 2 * i);
+                const double2 zv = ld2(z + 2 * i);
+                uv.x = __dsub_rn(uv.x, zv.x);
+                uv.y = __dsub_rn(uv.y, zv.y);
+                st2(u + 2 * i, uv);
+            }
         }
-        grid_barrier(a.bar);
-        ++n;
+        grid_barrier(cg.bar);
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counters_out != nullptr) {
-        a.counters_out[0] += s_newton;
-        a.counters_out[1] += s_linear;
+        int nn = 0, nl = 0;
+        for (int b = 0; b < B; ++b) {
+            nn += s_newton[b];
+            nl += s_linear[b];
+        }
+        a.counters_out[0] += nn;
+        a.counters_out[1] += nl;
     }
 }
 
@@ -555,59 +621,6 @@ SlabWorkLayout slab_work_layout(int n, int nz_max, int nfields) {
     return w;
 }
 
-template <int NDIM, bool SLAB>
-int pipe_grid(int* out) {
-    static int cached = 0;
-    if (cached == 0) {
-        SDC_CUDA_OK(cudaFuncSetAttribute(cg_pipe_kernel<NDIM, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(PipeSmem)));
-        int per_sm = 0;
-        SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_pipe_kernel<NDIM, SLAB>, kPipeThreads,
-                                                                  sizeof(PipeSmem)));
-        if (per_sm < 1) return fail("pipe_grid", "pipelined solver kernel does not fit on an SM");
-        if (per_sm > 2) per_sm = 2;
-        cached = per_sm * sm_count();
-    }
-    *out = cached;
-    return 0;
-}
-
-// ---- tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda) ------------
-typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int tensor_map_encoder(TensorMapEncodeFn* out) {
-    static TensorMapEncodeFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        SDC_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (p == nullptr || q != cudaDriverEntryPointSuccess)
-            return fail("tensor_map_encoder", "the CUDA driver does not provide cuTensorMapEncodeTiled");
-        fn = reinterpret_cast<TensorMapEncodeFn>(p);
-    }
-    *out = fn;
-    return 0;
-}
-
-// Tiled fp64 map over a walled field: 2-D  {P, P} from element (0,0);  3-D  {P, P, nz+2} starting ONE PLANE BELOW the
-// field (guard = lower halo plane) up to and including plane nz (wall / upper halo plane).
-int encode_field_map(CUtensorMap* map, const Geom& g, const double* field, int box_x, int box_y) {
-    TensorMapEncodeFn enc = nullptr;
-    if (int rc = tensor_map_encoder(&enc)) return rc;
-    const cuuint32_t rank = (cuuint32_t)g.ndim;
-    cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.P, (cuuint64_t)(g.nz + 2)};
-    cuuint64_t strides[2] = {(cuuint64_t)g.sy * 8u, (cuuint64_t)g.sz * 8u};
-    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1u};
-    cuuint32_t estr[3] = {1u, 1u, 1u};
-    void* base = const_cast<double*>(g.ndim == 3 ? field - g.sz : field);
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("encode_field_map", "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-    return 0;
-}
-
 // Degree-1 Chebyshev polynomial preconditioner for M = m_diag I + m_off S (S = sum of the 2*ndim neighbours, spectrum
 // inside (-2 ndim, 2 ndim)): two steps of the Chebyshev semi-iteration for M z = r from z = 0 give
 // z = pc_a r + pc_b M r.  It roughly halves the CG iteration count at the price of one more stencil pass per iteration.
@@ -625,27 +638,20 @@ inline void chebyshev1(int ndim, double m_diag, double m_off, double* pc_a, doub
     *pc_b = -2.0 * rho1 / (delta * theta);
 }
 
-template <int NDIM, bool SLAB = false>
+template <int NDIM, bool SLAB = false, bool PER = false>
 int launch_cg_pipe(CgArgs& cg, cudaStream_t s, const SlabLink* link = nullptr) {
     int grid = 0;
-    if (int rc = pipe_grid<NDIM, SLAB>(&grid)) return rc;
+    const size_t smem = sizeof(PipeSmemT<PER, false>);
+    if (int rc = pipe_grid<cg_pipe_kernel<NDIM, SLAB, PER>>(smem, &grid)) return rc;
     if (grid > kMaxGrid) grid = kMaxGrid;
-    static thread_local PipeArgs a;  // 6 KB: kept off the stack
+    static thread_local PipeArgs a;  // ~16 KB: kept off the stack
     a.cg = cg;
     if (link != nullptr) a.link = *link;
-    for (int b = 0; b < cg.B; ++b) {
-        const Sys& S = cg.s[b];
-        if (int rc = encode_field_map(&a.maps.m[b][kMapRHalo], cg.g, S.r, kPHX, kPHY)) return rc;
-        if (int rc = encode_field_map(&a.maps.m[b][kMapPHalo], cg.g, S.p, kPHX, kPHY)) return rc;
-        if (int rc = encode_field_map(&a.maps.m[b][kMapQHalo], cg.g, S.q, kPHX, kPHY)) return rc;
-        if (int rc = encode_field_map(&a.maps.m[b][kMapRCentre], cg.g, S.r, kPX, kPY)) return rc;
-        if (int rc = encode_field_map(&a.maps.m[b][kMapXCentre], cg.g, S.x, kPX, kPY)) return rc;
-        if (S.z != nullptr)
-            if (int rc = encode_field_map(&a.maps.m[b][kMapZHalo], cg.g, S.z, kPHX, kPHY)) return rc;
-    }
+    for (int b = 0; b < cg.B; ++b)
+        if (int rc = encode_system_maps(a.maps.m[b], cg.g, cg.s[b])) return rc;
     void* params[] = {&a};
-    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_pipe_kernel<NDIM, SLAB>, dim3(grid), dim3(kPipeThreads), params,
-                                            sizeof(PipeSmem), s));
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)cg_pipe_kernel<NDIM, SLAB, PER>, dim3(grid), dim3(kPipeThreads), params,
+                                            smem, s));
     return 0;
 }
 
@@ -673,7 +679,7 @@ int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas)
     if (cc_major) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc_minor) SDC_CUDA_OK(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
     if (solver_ctas) {
-        if (int rc = pipe_grid<3, false>(solver_ctas)) return rc;
+        if (int rc = pipe_grid<cg_pipe_kernel<3, false, false>>(sizeof(PipeSmemT<false, false>), solver_ctas)) return rc;
     }
     return 0;
 }
@@ -726,11 +732,10 @@ int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_h
     SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
     int rc = 1;
     const bool per = a.g.periodic;
+    // 2-D / 3-D grids: bulk-async pipelined passes (periodic grids with wrap sets); 1-D: register-marching passes
     if (ndim == 1) rc = per ? launch_cg<1, true>(a, s) : launch_cg<1, false>(a, s);
-    // heat solves on Dirichlet grids (the 2-D / 3-D benchmark configurations): bulk-async pipelined passes;
-    // periodic and 1-D grids: register-marching passes
-    if (ndim == 2) rc = per ? launch_cg<2, true>(a, s) : launch_cg_pipe<2>(a, s);
-    if (ndim == 3) rc = per ? launch_cg<3, true>(a, s) : launch_cg_pipe<3>(a, s);
+    if (ndim == 2) rc = per ? launch_cg_pipe<2, false, true>(a, s) : launch_cg_pipe<2>(a, s);
+    if (ndim == 3) rc = per ? launch_cg_pipe<3, false, true>(a, s) : launch_cg_pipe<3>(a, s);
     return rc;
 }
 
@@ -806,55 +811,68 @@ int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const d
             L.hi_r_halo[b] = reinterpret_cast<double*>(static_cast<char*>(work_of_rank[rank + 1]) + off_r) - sz;
     }
     SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
-    return launch_cg_pipe<3, true>(a, s, &L);
+    return launch_cg_pipe<3, true, false>(a, s, &L);
 }
 
-size_t sdcb200_newton_workspace_bytes(int n) { return work_layout(2, n, 6).total; }
+size_t sdcb200_newton_workspace_bytes(int n, int B) { return work_layout(2, n, 6 * B).total; }
 
-int sdcb200_allencahn_newton_solve(int n, double factor, double a_diag, double a_off, double inv_eps2, int nu_exp,
-                                   const double* rhs, double* u, double newton_tol, int newton_maxiter,
-                                   double lin_tol, int lin_maxiter, double inexact_ratio, void* work,
+int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, double a_diag, double a_off, double inv_eps2,
+                                   int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
+                                   int newton_maxiter, double lin_tol, int lin_maxiter, double inexact_ratio, void* work,
                                    size_t work_bytes, int* counters_dev, void* stream) {
     SDC_REQUIRE(n >= 2 && !(n & 1), "periodic grid needs an even number of points per dimension");
     SDC_REQUIRE(nu_exp >= 1, "nu must be a positive integer");
-    const WorkLayout w = work_layout(2, n, 6);
+    SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES, "B out of range");
+    const WorkLayout w = work_layout(2, n, 6 * B);
     SDC_REQUIRE(work != nullptr && work_bytes >= w.total, "workspace too small (see sdcb200_newton_workspace_bytes)");
     SDC_REQUIRE((reinterpret_cast<size_t>(work) & 255u) == 0, "workspace must be 256-byte aligned");
-    SDC_REQUIRE(rhs && u && !(reinterpret_cast<size_t>(rhs) & 15u) && !(reinterpret_cast<size_t>(u) & 15u),
-                "rhs / u missing or misaligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    NewtonArgs a;
-    memset(&a, 0, sizeof(a));
-    a.g = make_geom(2, n, SDCB200_BC_PERIODIC);
-    a.factor = factor;
+    static thread_local NewtonPipeArgs npa;
+    memset(&npa.nw, 0, sizeof(npa.nw));
+    NewtonArgs& a = npa.nw;
+    a.cg.g = make_geom(2, n, SDCB200_BC_PERIODIC);
+    a.cg.B = B;
+    a.cg.maxiter = lin_maxiter;
     a.a_diag = a_diag;
     a.a_off = a_off;
     a.inv_eps2 = inv_eps2;
     a.nu_exp = nu_exp;
-    a.rhs = rhs;
-    a.u = u;
     char* base = static_cast<char*>(work);
-    auto fieldp = [&](int k) { return reinterpret_cast<double*>(base + w.fields_off + (size_t)k * w.field + w.guard_bytes); };
-    a.gvec = fieldp(0);
-    a.z = fieldp(1);
-    a.dvec = fieldp(2);
-    a.r = fieldp(3);
-    a.p = fieldp(4);
-    a.q = fieldp(5);
+    for (int b = 0; b < B; ++b) {
+        SDC_REQUIRE(rhs[b] && u[b] && !(reinterpret_cast<size_t>(rhs[b]) & 15u) && !(reinterpret_cast<size_t>(u[b]) & 15u),
+                    "rhs / u missing or misaligned");
+        auto fieldp = [&](int k) {
+            return reinterpret_cast<double*>(base + w.fields_off + (size_t)(6 * b + k) * w.field + w.guard_bytes);
+        };
+        a.ns[b].rhs = rhs[b];
+        a.ns[b].u = u[b];
+        a.ns[b].factor = factor_host[b];
+        Sys& S = a.cg.s[b];
+        S.b = fieldp(0);     // Newton residual g
+        S.x = fieldp(1);     // Newton update z
+        S.dvec = fieldp(2);  // Jacobian diagonal
+        S.r = fieldp(3);
+        S.p = fieldp(4);
+        S.q = fieldp(5);
+        S.m_diag = 0.0;
+        S.m_off = -(factor_host[b] * a_off);
+        if (int rc = encode_system_maps(npa.maps.m[b], a.cg.g, S)) return rc;
+    }
     a.newton_tol = newton_tol;
     a.lin_tol = lin_tol;
     a.inexact_ratio = inexact_ratio;
     a.newton_maxiter = newton_maxiter;
     a.lin_maxiter = lin_maxiter;
-    a.partials = reinterpret_cast<double*>(base + w.partials_off);
-    a.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
+    a.cg.partials = reinterpret_cast<double*>(base + w.partials_off);
+    a.cg.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
     a.counters_out = counters_dev;
-    SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    SDC_CUDA_OK(cudaMemsetAsync(a.cg.bar, 0, 256, s));
     int grid = 0;
-    if (int rc = coresident_ctas(newton_kernel, &grid)) return rc;
+    const size_t smem = sizeof(PipeSmemT<true, true>);
+    if (int rc = pipe_grid<newton_pipe_kernel>(smem, &grid)) return rc;
     if (grid > kMaxGrid) grid = kMaxGrid;
-    void* params[] = {&a};
-    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)newton_kernel, dim3(grid), dim3(kThreads), params, 0, s));
+    void* params[] = {&npa};
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)newton_pipe_kernel, dim3(grid), dim3(kPipeThreads), params, smem, s));
     return 0;
 }
 

@@ -29,23 +29,21 @@ struct CgArgs {
     int* iters_out;    // [B], += iterations
 };
 
-struct NewtonArgs {
-    Geom g;
-    double factor, a_diag, a_off, inv_eps2;
-    int nu_exp;
+// Batched Allen-Cahn Newton solves: system b solves  u - factor_b (A u + 1/eps^2 u (1 - u^nu)) = rhs_b  for u_b.  The
+// inner CG systems (right-hand side g_b, solution z_b, Jacobian diagonal d_b, work fields) are described by CgArgs.s[b].
+struct NewtonSys {
     const double* rhs;
     double* u;
-    double* gvec;  // Newton residual
-    double* z;     // Newton update (CG solution)
-    double* dvec;  // Jacobian diagonal
-    double* r;
-    double* p;
-    double* q;
+    double factor;
+};
+struct NewtonArgs {
+    CgArgs cg;     // g, B, s[b] = {b: g_b, x: z_b, r, p, q, dvec: d_b (written by the kernel), m_off}, partials, bar
+    NewtonSys ns[SDCB200_MAX_NODES];
+    double a_diag, a_off, inv_eps2;
+    int nu_exp;
     double newton_tol, lin_tol, inexact_ratio;
     int newton_maxiter, lin_maxiter;
-    double* partials;
-    unsigned* bar;
-    int* counters_out;  // [0] += newton iterations, [1] += CG iterations
+    int* counters_out;  // [0] += newton iterations, [1] += CG iterations (summed over the systems)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -69,9 +67,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar) {
 
 // Per-CTA partial sums live in kPartialSlots areas of [MAX_NODES][gridDim.x] doubles.  A slot may only be rewritten
 // after a grid barrier that every CTA enters AFTER its last read of the slot, so consecutive reductions never share a
-// slot: pass A uses 0, pass B 1, pass C (preconditioner) 2, the set-up pass 3 and 4 (written once per solve).
-constexpr int kPartialSlots = 5;
-enum { kSlotA = 0, kSlotB = 1, kSlotC = 2, kSlotSetup0 = 3, kSlotSetup1 = 4 };
+// slot: pass A uses 0, pass B 1, pass C (preconditioner) 2, the set-up pass 3 and 4 (written once per solve), the Newton
+// residual norm 5.
+constexpr int kPartialSlots = 6;
+enum { kSlotA = 0, kSlotB = 1, kSlotC = 2, kSlotSetup0 = 3, kSlotSetup1 = 4, kSlotNewton = 5 };
 
 // Sum the per-CTA partials of one quantity in a fixed order; identical bits in every thread of every CTA.
 __device__ __forceinline__ double grid_sum(const double* partials, int slot, int b, double* scratch) {
@@ -145,6 +144,7 @@ struct CgShared {
     double bb[SDCB200_MAX_NODES], rr[SDCB200_MAX_NODES], rho_prev[SDCB200_MAX_NODES];
     double rz[SDCB200_MAX_NODES];  // r.z of the preconditioned solver (== rr without a preconditioner)
     double alpha[SDCB200_MAX_NODES], beta[SDCB200_MAX_NODES];
+    double rtol[SDCB200_MAX_NODES];  // relative tolerance of each system (set by the caller of the collective solver)
     int iters[SDCB200_MAX_NODES];
     unsigned active;  // bit b set: system b still iterating
 };

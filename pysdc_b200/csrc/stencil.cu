@@ -1,5 +1,5 @@
 // K2: right-hand side evaluation (eval_f) for the FD heat equation and the fully implicit Allen-Cahn problem.
-#include "stencil.cuh"
+#include "pipe_host.cuh"
 
 namespace sdcb200 {
 namespace {
@@ -62,13 +62,74 @@ int launch_eval(const EvalArgs& a, cudaStream_t s) {
     return 0;
 }
 
+// ---- 2-D / 3-D grids: the same evaluation as a TMA-pipelined pass (phase F of cg_pipe.cuh): a producer warp streams
+// the planes of u (with halo; periodic grids: wrap boxes) and of the forcing profile through shared memory, 8 consumer
+// warps evaluate the stencil from there - enough bytes in flight to keep HBM busy where the register-marching loader
+// tops out at ~70 % of the copy bandwidth.
+struct EvalPipeArgs {
+    Geom g;
+    int B;
+    EvalPhase ev;
+    PipeMaps maps;
+};
+
+template <int NDIM, bool PER>
+__global__ void __maxnreg__(112) eval_pipe_kernel(const __grid_constant__ EvalPipeArgs a) {
+    using Smem = PipeSmemT<PER, false>;
+    extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
+    __shared__ CgShared sh;  // not used by this phase (no reductions)
+    pipe_ctl_init(sm.ctl, PipeCfg<PER, false>::kStages);
+    if (threadIdx.x == 0) {
+        sm.ctl.nact = a.B;
+        for (int b = 0; b < a.B; ++b) sm.ctl.act_list[b] = b;
+    }
+    __syncthreads();
+    const PUnits PU = make_punits(a.g, a.B, (int)gridDim.x);
+    unsigned kstep = 0;
+    PassArgs pa;
+    pa.ev = &a.ev;
+    pipe_pass<NDIM, PER, false, kPhaseF>(a.g, PU, nullptr, a.maps, sh, sm, nullptr, kstep, pa);
+}
+
+template <int NDIM, bool PER>
+int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
+    static thread_local EvalPipeArgs a;
+    const size_t smem = sizeof(PipeSmemT<PER, false>);
+    int ctas = 0;
+    if (int rc = pipe_grid<eval_pipe_kernel<NDIM, PER>>(smem, &ctas)) return rc;
+    for (int b0 = 0; b0 < e.B; b0 += SDCB200_MAX_NODES) {  // at most MAX_NODES fields per launch (M + 1 fields in predict)
+        const int nb = e.B - b0 < SDCB200_MAX_NODES ? e.B - b0 : SDCB200_MAX_NODES;
+        a.g = e.g;
+        a.B = nb;
+        a.ev.a_diag = e.a_diag;
+        a.ev.a_off = e.a_off;
+        a.ev.inv_eps2 = e.inv_eps2;
+        a.ev.nu_exp = e.nu_exp;
+        for (int b = 0; b < nb; ++b) {
+            a.ev.e[b].f = e.f[b0 + b];
+            a.ev.e[b].f_expl = e.profile != nullptr ? e.fexpl[b0 + b] : nullptr;
+            a.ev.e[b].gt = e.gt[b0 + b];
+            if (int rc = encode_halo_maps(a.maps.m[b], kMapPHalo, e.g, e.u[b0 + b])) return rc;
+            if (e.profile != nullptr)
+                if (int rc = encode_field_map(a.maps.m[b] + kMapDCentre, e.g, e.profile, kPX, kPY)) return rc;
+        }
+        const PUnits PU = make_punits(e.g, nb, ctas);
+        const long long units = (long long)nb * PU.per_field;
+        const int grid = (int)(units < ctas ? units : ctas);
+        eval_pipe_kernel<NDIM, PER><<<grid, kPipeThreads, smem, s>>>(a);
+        SDC_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
 template <int MODE>
 int dispatch_eval(const EvalArgs& a, cudaStream_t s) {
     const bool per = a.g.periodic;
     switch (a.g.ndim) {
         case 1: return per ? launch_eval<1, true, MODE>(a, s) : launch_eval<1, false, MODE>(a, s);
-        case 2: return per ? launch_eval<2, true, MODE>(a, s) : launch_eval<2, false, MODE>(a, s);
-        case 3: return per ? launch_eval<3, true, MODE>(a, s) : launch_eval<3, false, MODE>(a, s);
+        case 2: return per ? launch_eval_pipe<2, true>(a, s) : launch_eval_pipe<2, false>(a, s);
+        case 3: return per ? launch_eval_pipe<3, true>(a, s) : launch_eval_pipe<3, false>(a, s);
     }
     return fail("dispatch_eval", "ndim must be 1, 2 or 3");
 }
@@ -154,7 +215,7 @@ int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2
         a.u[b] = u[b];
         a.f[b] = f[b];
     }
-    return launch_eval<2, true, 2>(a, static_cast<cudaStream_t>(stream));
+    return launch_eval_pipe<2, true>(a, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -326,7 +326,7 @@ class AllenCahnMixin:
         self._be = get_backend()
         self._lay = get_layout(nvars)
         self._counters = self._be.zeros(6, dtype=torch.int32)  # [newton, linear, rhs(unused), -, per-launch newton, linear]
-        self._work = None
+        self._work = {}
         self.newton_itercount = 0  # kept for API compatibility; the live counts are in work_counters
         self.lin_itercount = 0
         self.newton_ncalls = 0
@@ -358,24 +358,26 @@ class AllenCahnMixin:
         return f
 
     def solve_system_batch(self, rhs, factors, xs, ts=None):
-        """Newton + inner CG per system, in place on xs (AllenCahn_2D_FD.py:137-205); one persistent launch each."""
-        if self._work is None:
-            self._work = self._be.newton_workspace(self._lay)
+        """Newton + inner CG for all given systems in ONE persistent launch, in place on xs
+        (AllenCahn_2D_FD.py:137-205; several systems = the independent node solves of a diagonal QDelta)."""
+        B = len(xs)
+        if B not in self._work:
+            self._work[B] = self._be.newton_workspace(self._lay, B)
         log = getattr(self, "solve_log", None)  # bench.py: per-launch device timing + iteration counts
-        for r, fac, x in zip(rhs, factors, xs):
-            counters = self._counters[4:6]
-            counters.zero_()
-            if log is not None:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            self._be.allencahn_newton_solve(self._lay, fac, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
-                                            r.flat, x.flat, self.newton_tol, self.newton_maxiter, self.lin_tol,
-                                            self.lin_maxiter, self.inexact_linear_ratio, self._work, counters)
-            if log is not None:
-                ev1.record()
-                log.append((ev0, ev1, counters.clone()))
-            self._counters[0:2] += counters
-            self.newton_ncalls += 1
+        counters = self._counters[4:6]
+        counters.zero_()
+        if log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        self._be.allencahn_newton_solve(self._lay, list(factors), self.a_diag, self.a_off, 1.0 / self.eps**2,
+                                        int(self.nu), [r.flat for r in rhs], [x.flat for x in xs], self.newton_tol,
+                                        self.newton_maxiter, self.lin_tol, self.lin_maxiter, self.inexact_linear_ratio,
+                                        self._work[B], counters)
+        if log is not None:
+            ev1.record()
+            log.append((ev0, ev1, counters.clone()))
+        self._counters[0:2] += counters
+        self.newton_ncalls += B
 
     def solve_system(self, rhs, factor, u0, t):
         me = self.dtype_u(u0)

@@ -244,7 +244,7 @@ class NumpyBackend:
     def cg_workspace(self, lay, B):
         return torch.zeros(8, dtype=torch.float64)
 
-    newton_workspace = lambda self, lay: torch.zeros(8, dtype=torch.float64)  # noqa: E731
+    newton_workspace = lambda self, lay, B: torch.zeros(8, dtype=torch.float64)  # noqa: E731
 
     @staticmethod
     def _cheb1(ndim, m_diag, m_off):
@@ -300,23 +300,24 @@ class NumpyBackend:
                 Mx[-1, 0] += m_off[b]
             self._grid(lay, x)[...] = np.linalg.solve(Mx, self._grid(lay, r))
 
-    def allencahn_newton_solve(self, lay, factor, a_diag, a_off, inv_eps2, nu_exp, rhs, u, newton_tol, newton_maxiter,
+    def allencahn_newton_solve(self, lay, factors, a_diag, a_off, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter,
                                lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
         self.launches += 1
-        x = self._grid(lay, u)
-        b = self._grid(lay, rhs)
-        n = 0
-        while n < newton_maxiter:
-            g = x - factor * (a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)) - b
-            res = np.max(np.abs(g))
-            if inexact_ratio:
-                lin_tol = res * inexact_ratio
-            if res < newton_tol:
-                break
-            d = 1.0 - factor * (a_diag + inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp))
-            mv = lambda v: d * v - factor * a_off * self._lap_sum(v, True)  # noqa: E731
-            z = np.zeros_like(x)
-            counters_dev[1] += self._cg(mv, g, z, lin_tol, lin_maxiter)
-            x -= z
-            n += 1
-        counters_dev[0] += n
+        for factor, r, u in zip(factors, rhs, us):
+            x = self._grid(lay, u)
+            b = self._grid(lay, r)
+            n, tol = 0, lin_tol
+            while n < newton_maxiter:
+                g = x - factor * (a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)) - b
+                res = np.max(np.abs(g))
+                if inexact_ratio:
+                    tol = res * inexact_ratio
+                if res < newton_tol:
+                    break
+                d = 1.0 - factor * (a_diag + inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp))
+                mv = lambda v: d * v - factor * a_off * self._lap_sum(v, True)  # noqa: E731
+                z = np.zeros_like(x)
+                counters_dev[1] += self._cg(mv, g, z, tol, lin_maxiter)
+                x -= z
+                n += 1
+            counters_dev[0] += n

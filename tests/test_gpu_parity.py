@@ -323,6 +323,51 @@ def test_allencahn_newton_against_oracle(oracle):
     assert pc.close_counts(P.work_counters["linear"].niter, O.counters["linear"].niter)
 
 
+def test_batched_newton_equals_sequential(oracle):
+    """Diagonal QDelta: the M Allen-Cahn node systems go through ONE Newton launch; every system must get exactly what
+    its own launch gives (same reduction trees, individual Newton / CG exits) and the oracle's solution."""
+    from pysdc_b200.problems import allencahn_fullyimplicit
+
+    pp = dict(nvars=(128, 128), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9, lin_tol=1e-10, lin_maxiter=100,
+              radius=0.25)
+    P, O = allencahn_fullyimplicit(**pp), oracle.AllenCahnFD(**pp)
+    u0 = O.u_exact(0.0)
+    f0 = O.eval_f(u0, 0.0)
+    factors = [2e-4, 1e-3, 3e-3]  # different Newton / CG iteration counts per system
+    rhs = [u0 + fac * f0 for fac in factors]
+    xb = [pc.to_mesh(P, u0) for _ in factors]
+    P.solve_system_batch([pc.to_mesh(P, r) for r in rhs], factors, xb)
+    newton_b, linear_b = P.work_counters["newton"].niter, P.work_counters["linear"].niter
+    want_newton = want_linear = 0
+    for fac, r, x in zip(factors, rhs, xb):
+        xs = P.solve_system(pc.to_mesh(P, r), fac, pc.to_mesh(P, u0), 0.0)
+        assert np.array_equal(xs.get(), x.get())
+        n0, l0 = O.counters["newton"].niter, O.counters["linear"].niter
+        assert pc.relerr(x.get(), O.solve_system(r, fac, u0, 0.0)) < pc.TOL_SOLVE
+        want_newton += O.counters["newton"].niter - n0
+        want_linear += O.counters["linear"].niter - l0
+    assert P.work_counters["newton"].niter == 2 * newton_b and P.work_counters["linear"].niter == 2 * linear_b
+    assert newton_b == want_newton and pc.close_counts(linear_b, want_linear)
+
+
+def test_allencahn_diagonal_sweeps_batch_the_node_solves(oracle):
+    """allencahn_fullyimplicit with MIN-SR-NS: node-batched Newton through the sweeper vs the oracle's sequential run."""
+    spec, _ = load_golden("run_allencahn_gi_lu_64")
+    spec = dict(spec, sweeper_params=dict(spec["sweeper_params"], QI="MIN-SR-NS"))
+    ref = oracle.run_sdc(spec)
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.stats import get_sorted
+
+    c = controller_nonMPI(1, {"logger_level": 40}, pc.make_description(spec))
+    P = c.MS[0].levels[0].prob
+    launches0 = P._be.launches
+    uend, stats = c.run(u0=P.u_exact(0.0), t0=spec["t0"], Tend=spec["Tend"])
+    assert [int(v) for _, v in get_sorted(stats, type="niter")] == ref["niter"]
+    assert pc.relerr(uend.get(), ref["uend"]) < pc.TOL_SOLVE
+    assert P.work_counters["newton"].niter == sum(ref["work"]["newton"])
+    assert P.newton_ncalls == 3 * sum(ref["niter"])  # three node systems per sweep, one launch per sweep
+
+
 def test_midsize_3d_run_against_oracle(oracle):
     """Config 3 at 63^3 with the bench settings (restol=-1, K=4 sweeps): residual history and solution vs the fixture of
     the reference and the oracle run on this host."""
