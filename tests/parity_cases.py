@@ -152,6 +152,24 @@ def check_sweep_dump(name):
             assert close_counts(P.work_counters[key].niter, want), (key, P.work_counters[key].niter, want)
 
 
+def sensitive_steps(name, ref_niter):
+    """Steps of a BASELINE-size fixture on which the UNMODIFIED reference does not hold its own SDC iteration count: runs
+    of the reference with rounding-level perturbations of its inputs, or with another BLAS thread count, recorded in
+    tests/golden/sensitivity_config*.json by oracle/sensitivity.py.  Only there may a count differ (by one)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    cfg = {"run_config2_heat2d_imex_lu_2047": "config2", "pfasst_config5_1023_p8": "config5"}.get(name)
+    path = os.path.join(GOLDEN, f"sensitivity_{cfg}.json")
+    if cfg is None or not os.path.exists(path):
+        return set()
+    with open(path) as f:
+        runs = json.load(f)["runs"]
+    return {i for r in runs for i, (a, b) in enumerate(zip(r["niter"], ref_niter)) if a != b}
+
+
 def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
     from pysdc_b200.controller import LogWork, controller_nonMPI
     from pysdc_b200.stats import get_sorted
@@ -166,19 +184,28 @@ def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
         u0 = to_mesh(P, np.random.default_rng(spec["seed"]).standard_normal(P.nvars))
     uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
     niter = [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")]
-    assert niter == g["niter"].tolist(), (niter, g["niter"].tolist())
+    want = g["niter"].tolist()
+    loose = sensitive_steps(name, want)  # empty for every fixture but the rounding-decided BASELINE-size ones
+    assert len(niter) == len(want) and all(a == b or (i in loose and abs(a - b) == 1)
+                                           for i, (a, b) in enumerate(zip(niter, want))), (niter, want, loose)
     times = [t for t, _ in get_sorted(stats, type="niter", sortby="time")]
-    for t, ref in zip(times, g["residuals"]):
+    for i, (t, ref) in enumerate(zip(times, g["residuals"])):
         hist = [v for _, v in get_sorted(stats, time=t, type="residual_post_iteration", sortby="iter")]
         ref = ref[~np.isnan(ref)]
-        assert len(hist) == len(ref)
-        # per-sweep residual histories agree to 1e-8 relative above the solver noise floor
-        np.testing.assert_allclose(hist, ref, rtol=1e-6, atol=2e-11 * max(1.0, float(g["uend_maxabs"])))
+        assert len(hist) == len(ref) or i in loose
+        k = min(len(hist), len(ref))
+        # per-sweep residual histories agree to 1e-8 relative above the solver noise floor (the
+        # BASELINE-size runs stagnate at ~1e-10, where the inner CG's rounding shows)
+        floor = (6e-11 if name.startswith("run_config") else 2e-11) * max(1.0, float(g["uend_maxabs"]))
+        np.testing.assert_allclose(hist[:k], ref[:k], rtol=1e-6, atol=floor)
     # error relative to the solution scale of the run (the initial value for strongly decaying solutions: the SDC
     # residual tolerance that terminates every step is absolute)
     scale = max(abs(u0), float(g["uend_maxabs"]))
     if "uend" in g:
         assert np.max(np.abs(uend.get() - g["uend"])) <= uend_tol * scale
+    if "uend_sub" in g:  # BASELINE-size fixtures keep a subsample of the end value
+        k = spec["subsample"]
+        assert np.max(np.abs(uend.get()[::k, ::k] - g["uend_sub"])) <= uend_tol * scale
     assert abs(abs(uend) - float(g["uend_maxabs"])) <= uend_tol * scale
     for key in P.work_counters:
         got = [int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")]
@@ -186,7 +213,11 @@ def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
         if key in ("newton", "rhs"):
             assert got == want, (key, got, want)
         elif count_slack is not None:
-            assert close_counts(got, want, count_slack), (key, got, want)
+            # BASELINE-size runs: thousands of CG iterations per step, each solve's count within a few of the reference's;
+            # a step that takes one sweep more or less (see sensitive_steps) is not comparable
+            keep = [i for i in range(len(want)) if i not in loose or niter[i] == g["niter"][i]]
+            slack = 0.04 if name.startswith("run_config") else count_slack
+            assert close_counts([got[i] for i in keep], [want[i] for i in keep], slack), (key, got, want)
     return dict(niter=niter, uend=uend, stats=stats)
 
 
