@@ -97,6 +97,51 @@ class LogWork(Hooks):
                               iter=step.status.iter, sweep=L.status.sweep, type=f"work_{key}")
 
 
+class LogToFile(Hooks):
+    """Solutions to a FieldsIO file every ``time_increment`` time units, as ``implementations/hooks/log_solution.py:
+    207-282`` does: the problem provides the file (``getOutputFile``) and the host copy (``processSolutionForOutput``,
+    an asynchronous device -> pinned-host copy here); an existing file is re-opened and continued when the run starts
+    at t > 0."""
+
+    filename = "myRun.pySDC"
+    time_increment = 0
+    counter = 0
+
+    def __init__(self):
+        super().__init__()
+        self.outfile, self.t_next_log = None, 0
+
+    def pre_run(self, step, level_number):
+        import os
+
+        L = step.levels[level_number]
+        if os.path.isfile(self.filename) and L.time > 0:
+            self.outfile = L.prob.openOutputFile(self.filename)
+        else:
+            self.outfile = L.prob.getOutputFile(self.filename)
+            self.outfile.addField(time=L.time, field=L.prob.processSolutionForOutput(L.u[0]))
+        type(self).counter = len(self.outfile.times)
+
+    def post_step(self, step, level_number):
+        L = step.levels[level_number]
+        if self.t_next_log == 0:
+            self.t_next_log = L.time + self.time_increment
+        if L.time + L.dt >= self.t_next_log:
+            self.outfile.addField(time=L.time + L.dt, field=L.prob.processSolutionForOutput(L.uend))
+            self.t_next_log = max([L.time + L.dt, self.t_next_log]) + self.time_increment
+            type(self).counter += 1  # (not len(outfile.times): that would wait for the copy that is still in flight)
+
+    def post_run(self, step, level_number):
+        self.outfile.flush()
+
+    @classmethod
+    def load(cls, index):
+        from .fields_io import RectilinearFile
+
+        t, u = RectilinearFile.fromFile(cls.filename).readField(index)
+        return {"t": t, "u": u}
+
+
 class controller_nonMPI:
     """``controller_nonMPI(num_procs, controller_params, description).run(u0, t0, Tend) -> (uend, stats)``."""
 
@@ -143,6 +188,10 @@ class controller_nonMPI:
         if not t < Tend - 10 * np.finfo(float).eps:
             raise ControllerError("Nothing to do, check t0, dt and Tend.")
         S.status.slot = 0
+        # the first block is set up before the pre-run hooks fire (controller_nonMPI.py:101-110): they may read L.u[0]
+        S.reset_step()
+        S.init_step(u0)
+        L.status.time = t0
         self._call("post_setup", S)
         self._call("pre_run", S)
         uend = u0

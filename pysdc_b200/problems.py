@@ -19,6 +19,7 @@ from .backend import get_backend
 from .datatypes import imex_mesh, mesh
 from .layout import get_layout
 from .errors import ProblemError
+from .fields_io import OutputMixin
 
 BC_CODES = {"dirichlet-zero": 0, "periodic": 1}
 
@@ -62,7 +63,7 @@ class DeviceWorkCounter:
 # ---------------------------------------------------------------------------------------------------------------------
 # heat equation
 # ---------------------------------------------------------------------------------------------------------------------
-class HeatMixin:
+class HeatMixin(OutputMixin):
     dtype_u = mesh
     dtype_f = mesh
     forced = False
@@ -297,7 +298,7 @@ class HeatForcedMixin(HeatMixin):
 # ---------------------------------------------------------------------------------------------------------------------
 # Allen-Cahn, fully implicit
 # ---------------------------------------------------------------------------------------------------------------------
-class AllenCahnMixin:
+class AllenCahnMixin(OutputMixin):
     dtype_u = mesh
     dtype_f = mesh
     forced = False

@@ -140,3 +140,34 @@ def test_second_residual_request_is_answered_from_the_first():
     n0 = be.launches
     L.sweep.compute_residual()
     assert be.launches == n0
+
+
+def test_output_file_of_device_fields(tmp_path):
+    """getOutputFile / processSolutionForOutput (core/problem.py:84-94) + the LogToFile hook: solutions
+    land in a FieldsIO Rectilinear file (helpers/fieldsIO.py:388-463 layout), the run can be continued into the same
+    file, and what is read back is what the run returned."""
+    from pysdc_b200.controller import LogToFile, controller_nonMPI
+    from pysdc_b200.fields_io import RectilinearFile
+
+    class Log(LogToFile):
+        filename = str(tmp_path / "heat.pySDC")
+
+    spec = dict(problem="heatNd_unforced", sweeper="generic_implicit",
+                problem_params=dict(nvars=[15, 15], nu=0.1, freq=[2, 2], bc="dirichlet-zero", solver_type="CG",
+                                    lintol=1e-12, liniter=1000),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"), level_params=dict(dt=0.01, restol=1e-9),
+                step_params=dict(maxiter=20))
+    c = controller_nonMPI(1, dict(logger_level=40, hook_class=[Log]), pc.make_description(spec))
+    P = c.MS[0].levels[0].prob
+    u0 = P.u_exact(0.0)
+    umid, _ = c.run(u0=u0, t0=0.0, Tend=0.02)
+    f = RectilinearFile.fromFile(Log.filename)
+    assert f.times == pytest.approx([0.0, 0.01, 0.02]) and f.gridSizes == [15, 15] and f.nVar == 1
+    np.testing.assert_array_equal(f.coords[0], P.xvalues)
+    assert np.array_equal(f.readField(0)[1][0], u0.get()) and np.array_equal(f.readField(-1)[1][0], umid.get())
+    # continue the run into the same file (LogToFile.pre_run re-opens it when t0 > 0)
+    uend, _ = c.run(u0=umid, t0=0.02, Tend=0.04)
+    assert Log.load(-1)["t"] == pytest.approx(0.04) and np.array_equal(Log.load(-1)["u"][0], uend.get())
+    assert RectilinearFile.fromFile(Log.filename).nFields == 5
+    with pytest.raises(FileExistsError):
+        P.getOutputFile(Log.filename)

@@ -136,3 +136,36 @@ def test_reference_hooks_work_on_device_fields(plugin):
     assert [v for _, v in get_sorted(stats, type="k")] == [v for _, v in get_sorted(stats, type="niter")]
     err = get_sorted(stats, type="e_global_post_run")[-1][1]
     assert err == pytest.approx(abs(P.u_exact(0.03) - uend)) and err < 1e-3
+
+
+def test_reference_LogToFile_hook_writes_device_fields(plugin, tmp_path):
+    """the reference's own LogToFile hook (hooks/log_solution.py:207-282) asks the plug-in problem for
+    getOutputFile / processSolutionForOutput; the file it writes is read back with the reference's FieldsIO, and the
+    hook's resume path (re-opening the file with FieldsIO.fromFile and appending staged device fields) works."""
+    from pySDC.helpers.fieldsIO import FieldsIO
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+    from pySDC.implementations.hooks.log_solution import LogToFile
+
+    class Log(LogToFile):
+        filename = str(tmp_path / "heat.pySDC")
+
+    d = dict(problem_class=plugin.heatNd_forced,
+             problem_params=dict(nvars=(15, 15), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-12,
+                                 liniter=1000),
+             sweeper_class=plugin.imex_1st_order, sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+             level_params=dict(dt=0.01, restol=1e-9), step_params=dict(maxiter=20))
+    c = controller_nonMPI(num_procs=1, controller_params=dict(logger_level=40, hook_class=[Log]), description=d)
+    P = c.MS[0].levels[0].prob
+    u0 = P.u_exact(0.0)
+    umid, _ = c.run(u0=u0, t0=0.0, Tend=0.02)
+    c.MS[0].levels[0].prob  # noqa: B018
+    del c  # (drops the hook and with it the file object: a pending device field is flushed)
+    import gc
+
+    gc.collect()
+    f = FieldsIO.fromFile(Log.filename)
+    assert f.times == pytest.approx([0.0, 0.01, 0.02]) and f.gridSizes == [15, 15]
+    assert np.array_equal(f.readField(0)[1][0], u0.get()) and np.array_equal(f.readField(-1)[1][0], umid.get())
+    c = controller_nonMPI(num_procs=1, controller_params=dict(logger_level=40, hook_class=[Log]), description=d)
+    uend, _ = c.run(u0=umid, t0=0.02, Tend=0.04)
+    assert Log.load(-1)["t"] == pytest.approx(0.04) and np.array_equal(Log.load(-1)["u"][0], uend.get())
