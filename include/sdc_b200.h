@@ -171,6 +171,23 @@ int sdcb200_axis_apply(long long n_outer, int n_out, long long n_inner, int widt
 int sdcb200_heat_direct_solve_1d(int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
                                  const double* const* rhs, double* const* x, void* stream);
 
+/* ---- higher-order stencils (order 4 / 6 / 8) ---------------------------------------------------------------------------
+ * A = nu * (Kronecker sum of the 1-D centred second-derivative stencil of the given order) / dx^2 as built by
+ * helpers/problem_helper.py:42-80,83-242: centre_host[k] (k = 0 .. order/2) are the centred coefficients (already
+ * scaled by nu/dx^2); on dirichlet-zero grids the order/2 rows next to each boundary use the reference's one-sided
+ * closure stencils, lo_host / hi_host = (order/2) x (order+1) coefficient rows acting on the first / last order+1
+ * points of a line (NULL on periodic grids).  eval_f and the CG node solves (I - factor_b A) x_b = rhs_b with the same
+ * persistent, node-batched, device-resident iteration as sdcb200_heat_cg_solve.  Replaces GenericNDimFinDiff.eval_f /
+ * solve_system for order > 2 (generic_ND_FD.py:188-264; tests/test_2d_fd_accuracy.py).                              */
+int sdcb200_heat_eval_f_ho(int ndim, int n, int bc, int order, const double* centre_host, const double* lo_host,
+                           const double* hi_host, int B, const double* const* u, double* const* f_impl,
+                           const double* profile, const double* gt_host, double* const* f_expl, void* stream);
+size_t sdcb200_cg_ho_workspace_bytes(int ndim, int n, int B);
+int sdcb200_heat_cg_solve_ho(int ndim, int n, int bc, int order, const double* centre_host, const double* lo_host,
+                             const double* hi_host, int B, const double* factor_host, const double* const* rhs,
+                             double* const* x, double rtol, int maxiter, void* work, size_t work_bytes, int* iters_dev,
+                             void* stream);
+
 /* ---- K4: Allen-Cahn Newton ------------------------------------------------------------------------------------------
  * Newton iteration with inner CG on the Jacobian for B node systems  u_b - factor_b (A u_b + 1/eps^2 u_b (1 - u_b^nu)) =
  * rhs_b, whole solve in one persistent launch (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205; B > 1:

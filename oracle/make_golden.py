@@ -300,12 +300,21 @@ def operator_vectors():
         ("heat3d_periodic", heatNd_unforced, dict(nvars=(16, 16, 16), nu=0.1, freq=(2, 2, 2), bc="periodic", solver_type="CG", lintol=1e-13)),
         ("heat2d_forced", heatNd_forced, dict(nvars=(31, 31), nu=0.1, freq=(4, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-13)),
         ("heat3d_forced", heatNd_forced, dict(nvars=(15, 15, 15), nu=0.1, freq=(1, 2, 3), bc="dirichlet-zero", solver_type="CG", lintol=1e-13)),
+        # higher-order stencils (helpers/problem_helper.py:19-21; dirichlet: one-sided closure rows, :157-201)
+        ("heat2d_periodic_o4", heatNd_unforced, dict(nvars=(32, 32), nu=0.1, freq=(2, 2), bc="periodic", order=4, solver_type="CG", lintol=1e-13)),
+        ("heat2d_periodic_o8", heatNd_unforced, dict(nvars=(32, 32), nu=0.1, freq=(2, 2), bc="periodic", order=8, solver_type="CG", lintol=1e-13)),
+        ("heat3d_periodic_o6", heatNd_unforced, dict(nvars=(16, 16, 16), nu=0.1, freq=(2, 2, 2), bc="periodic", order=6, solver_type="CG", lintol=1e-13)),
+        ("heat1d_dirichlet_o8", heatNd_unforced, dict(nvars=63, nu=0.7, freq=2, bc="dirichlet-zero", order=8, solver_type="CG", lintol=1e-13)),
+        ("heat2d_dirichlet_o4", heatNd_forced, dict(nvars=(31, 31), nu=0.1, freq=(4, 2), bc="dirichlet-zero", order=4, solver_type="CG", lintol=1e-13)),
+        ("heat3d_dirichlet_o6", heatNd_unforced, dict(nvars=(15, 15, 15), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", order=6, solver_type="CG", lintol=1e-13)),
     ]:
         P = cls(**pp)
+        # (the higher-order cases were added later: own generator, so that the earlier fixtures regenerate unchanged)
+        gen = np.random.default_rng(3000 + pp["order"]) if "order" in pp else rng
         u = P.u_init
-        u[:] = rng.standard_normal(u.shape)
+        u[:] = gen.standard_normal(u.shape)
         rhs = P.u_init
-        rhs[:] = rng.standard_normal(u.shape)
+        rhs[:] = gen.standard_normal(u.shape)
         t, factor = 0.37, 0.0123
         f = P.eval_f(u, t)
         sol = P.solve_system(rhs, factor, u, t)

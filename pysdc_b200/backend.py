@@ -54,6 +54,10 @@ def _declare(lib):
         "sdcb200_heat_eval_f_slab": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_axis_apply": (c_int, [c_ll, c_int, c_ll, c_int, _c_dp, _c_dp, _c_dp, c_ll, c_ll, _c_dp, c_ll, c_ll, _c_dp]),
         "sdcb200_heat_direct_solve_1d": (c_int, [c_int, c_int, c_int, PD, PD, PP, PP, _c_dp]),
+        "sdcb200_heat_eval_f_ho": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
+        "sdcb200_cg_ho_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "sdcb200_heat_cg_solve_ho": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_int, PD, PP, PP, c_d, c_int, _c_dp,
+                                             c_sz, _c_dp, _c_dp]),
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int, c_int]),
         "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
                                                    c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
@@ -195,6 +199,32 @@ class CudaBackend:
             lay.ndim, lay.n, bc, len(xs), _dbl_array(m_diag), _dbl_array(m_off), _ptr_array(rhs), _ptr_array(xs),
             float(rtol), int(maxiter), int(precond), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(),
             self._stream()))
+
+    # -- higher-order stencils (order 4 / 6 / 8) ------------------------------------------------------------------------
+    @staticmethod
+    def _ho_tables(op):
+        lo = None if op["lo"] is None else _dbl_array(op["lo"])
+        hi = None if op["hi"] is None else _dbl_array(op["hi"])
+        return _dbl_array(op["centre"]), lo, hi
+
+    def heat_eval_f_ho(self, lay, bc, op, us, fs, profile=None, gts=None, fexpls=None):
+        self.launches += 1
+        c, lo, hi = self._ho_tables(op)
+        self._check(self.lib.sdcb200_heat_eval_f_ho(
+            lay.ndim, lay.n, bc, op["order"], c, lo, hi, len(us), _ptr_array(us), _ptr_array(fs),
+            None if profile is None else profile.data_ptr(), None if gts is None else _dbl_array(gts),
+            None if fexpls is None else _ptr_array(fexpls), self._stream()))
+
+    def cg_ho_workspace(self, lay, B):
+        nbytes = self.lib.sdcb200_cg_ho_workspace_bytes(lay.ndim, lay.n, B)
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def heat_cg_solve_ho(self, lay, bc, op, factors, rhs, xs, rtol, maxiter, work, iters_dev):
+        self.launches += 1
+        c, lo, hi = self._ho_tables(op)
+        self._check(self.lib.sdcb200_heat_cg_solve_ho(
+            lay.ndim, lay.n, bc, op["order"], c, lo, hi, len(xs), _dbl_array(factors), _ptr_array(rhs), _ptr_array(xs),
+            float(rtol), int(maxiter), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
 
     # -- slab-decomposed solves over peer-mapped memory -----------------------------------------------------------------
     def slab_cg_workspace(self, lay, comm, B):

@@ -114,8 +114,10 @@ struct PUnits {
     int nxt, nyt, nzc, chunk_z, per_field;
 };
 
-// Tile grid of the pipelined passes; the z-chunk is the longest march whose units (pooled over the B systems) still
-// fill whole waves of the persistent grid.
+// Tile grid of the pipelined passes.  The z-chunk trades re-read halo planes (2 per chunk and field read with halo)
+// against how evenly the units fill the waves of the persistent grid: take the longest march among the candidates whose
+// fill is within 2 % of the best one.  (Thin slabs - 64 planes per rank at 8 GPUs - give the same fill for every
+// candidate, so the whole slab is marched in one go instead of re-reading 12.5 % halo planes with 16-plane chunks.)
 __host__ __device__ inline PUnits make_punits(const Geom& g, int B, int ctas) {
     PUnits u;
     u.nxt = (g.P + kPX - 1) / kPX;
@@ -124,15 +126,23 @@ __host__ __device__ inline PUnits make_punits(const Geom& g, int B, int ctas) {
     u.nzc = 1;
     if (g.ndim == 3) {
         const int tiles = u.nxt * u.nyt;
+        double best = 0.0;
+        for (int c = 128; c >= 16; c >>= 1) {
+            const long long units = (long long)B * tiles * ((g.nz + c - 1) / c);
+            const long long rounds = (units + ctas - 1) / ctas;
+            const double fill = (double)units / (double)(rounds * ctas);
+            if (fill > best) best = fill;
+        }
         int chunk = 16;
         for (int c = 128; c >= 16; c >>= 1) {
             const long long units = (long long)B * tiles * ((g.nz + c - 1) / c);
             const long long rounds = (units + ctas - 1) / ctas;
-            if (rounds >= 3 && (double)units / (double)(rounds * ctas) > 0.92) {
+            if ((double)units / (double)(rounds * ctas) >= best - 0.02) {
                 chunk = c;
                 break;
             }
         }
+        if (chunk > g.nz) chunk = g.nz < 16 ? 16 : ((g.nz + 15) / 16) * 16;
         u.chunk_z = chunk;
         u.nzc = (g.nz + chunk - 1) / chunk;
     }

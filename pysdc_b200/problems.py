@@ -38,6 +38,44 @@ def grid_1d(size, bc, left=0.0, right=1.0):
     return dx, x
 
 
+def fd_weights(derivative, offsets):
+    """Finite-difference weights on the given integer offsets from the Taylor system, solved the way the reference
+    solves it (helpers/problem_helper.py:42-80) so that the coefficients are the reference's floats."""
+    from scipy.special import factorial
+
+    steps = np.asarray(offsets)
+    n = len(steps)
+    A = np.zeros((n, n))
+    idx = np.arange(n)
+    inv_facs = 1.0 / factorial(idx)
+    for i in range(n):
+        A[i, :] = steps ** idx[i] * inv_facs[i]
+    sol = np.zeros(n)
+    sol[derivative] = 1.0
+    coeff = np.linalg.solve(A, sol)
+    return coeff[np.argsort(steps)], np.sort(steps)
+
+
+def high_order_tables(order, bc, scale):
+    """Coefficient tables of the centred second-derivative stencil of the given order, times ``scale`` (= nu / dx^2):
+    ``centre[k]``, k = 0 .. order/2, and - dirichlet-zero - the one-sided closure rows of the order/2 points next to
+    each boundary (helpers/problem_helper.py:157-201 with the default ``reduce=False``; the coefficient of the boundary
+    value itself drops out because that value is zero): ``lo[i]`` acts on columns 0 .. order, ``hi[i]`` (row n-1-i) on
+    the last order+1 columns."""
+    h = order // 2
+    w, _ = fd_weights(2, np.arange(order + 1) - h)
+    tables = dict(order=order, centre=[float(w[h + k]) * scale for k in range(h + 1)], lo=None, hi=None)
+    if bc != "periodic":
+        lo, hi = np.zeros((h, order + 1)), np.zeros((h, order + 1))
+        for i in range(h):
+            cl, _ = fd_weights(2, np.arange(-(i + 1), order + 2 - (i + 1)))
+            cr, _ = fd_weights(2, np.arange(-(order + 2) + (i + 2), (i + 2)))
+            lo[i] = cl[1:] * scale
+            hi[i] = cr[:-1] * scale
+        tables.update(lo=lo, hi=hi)
+    return tables
+
+
 class DeviceWorkCounter:
     """``WorkCounter`` (core/problem.py:16-40) whose count lives in a device int: the solver kernels add their
     iteration counts without a host round trip; reading ``niter`` synchronises."""
@@ -105,9 +143,13 @@ class HeatMixin(OutputMixin):
         # what the device path implements
         if bc not in BC_CODES:
             raise ProblemError(f"boundary condition {bc!r} is not implemented on the device (have {list(BC_CODES)})")
-        if order != 2 or stencil_type != "center":
-            raise ProblemError("the device stencil is the order-2 centred Laplacian; "
+        if order not in (2, 4, 6, 8) or stencil_type != "center":
+            raise ProblemError("the device stencils are the centred Laplacians of order 2, 4, 6 and 8; "
                                f"got order={order}, stencil_type={stencil_type!r}")
+        if order != 2 and (solver_type == "direct" or preconditioner is not None or comm is not None):
+            raise ProblemError("order > 2 is implemented with solver_type='CG', without preconditioner and on one GPU")
+        if order != 2 and any(nv <= order for nv in nvars):
+            raise ProblemError(f"grid too small for the order-{order} stencil")
         if solver_type not in ("CG", "direct"):
             raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device (have 'CG', 'direct')")
         if solver_type == "direct" and ndim > 1:
@@ -136,6 +178,10 @@ class HeatMixin(OutputMixin):
         self.a_diag = ((-2.0 * ndim) / dx**2) * nu
         self._bc = BC_CODES[bc]
         self._be = get_backend()
+        # order > 2: wide stencils with the reference's boundary closures (highorder.cu); a_diag stays the diagonal of A
+        self._ho = None if order == 2 else high_order_tables(order, bc, (1.0 / dx**2) * nu)
+        if self._ho is not None:
+            self.a_diag = ndim * self._ho["centre"][0]
         self._precond = 1 if preconditioner == "chebyshev" else 0
         self._comm = comm if slab else None
         self._lay = comm.slab_layout(nvars) if slab else get_layout(nvars)
@@ -188,6 +234,12 @@ class HeatMixin(OutputMixin):
 
     def eval_f_batch(self, us, ts, fs):
         """fs[i] = f(us[i], ts[i]) in place, one launch for all fields."""
+        if self._ho is not None:
+            args = (self._spatial_profile().flat, [self._forcing_factor(t) for t in ts],
+                    [f.expl.flat for f in fs]) if self.forced else ()
+            self._be.heat_eval_f_ho(self._lay, self._bc, self._ho, [u.flat for u in us],
+                                    [(f.impl if self.forced else f).flat for f in fs], *args)
+            return
         if self._comm is not None:
             self._comm.exchange_halos(us)
         if self.forced:
@@ -207,7 +259,9 @@ class HeatMixin(OutputMixin):
     # -- implicit solves ----------------------------------------------------------------------------------------------
     def _cg_work(self, B):
         if B not in self._work:
-            if self._comm is not None:
+            if self._ho is not None:
+                self._work[B] = self._be.cg_ho_workspace(self._lay, B)
+            elif self._comm is not None:
                 self._work[B] = self._be.slab_cg_workspace(self._lay, self._comm, B)
             else:
                 self._work[B] = self._be.cg_workspace(self._lay, B)
@@ -228,7 +282,10 @@ class HeatMixin(OutputMixin):
         if log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if self._comm is not None:
+        if self._ho is not None:
+            self._be.heat_cg_solve_ho(self._lay, self._bc, self._ho, list(factors), [r.flat for r in rhs],
+                                      [x.flat for x in xs], self.lintol, self.liniter, self._cg_work(len(xs)), counters)
+        elif self._comm is not None:
             # the initial guesses need their neighbours' boundary planes; the solver exchanges everything else itself
             work = self._cg_work(len(xs))
             self._comm.exchange_halos(xs)

@@ -158,6 +158,49 @@ class NumpyBackend:
     def slab_cg_workspace(self, lay, comm, B):
         return None
 
+    # ---- higher-order stencils: dense 1-D operators applied axis by axis -----------------------------------------------
+    @staticmethod
+    def _ho_matrix(op, n, periodic):
+        h, order = op["order"] // 2, op["order"]
+        A = np.zeros((n, n))
+        for i in range(n):
+            for k in range(-h, h + 1):
+                j = i + k
+                if periodic:
+                    A[i, j % n] += op["centre"][abs(k)]
+                elif 0 <= j < n:
+                    A[i, j] += op["centre"][abs(k)]
+        if not periodic:
+            for i in range(h):
+                A[i, :] = 0.0
+                A[i, : order + 1] = op["lo"][i]
+                A[n - 1 - i, :] = 0.0
+                A[n - 1 - i, n - order - 1:] = op["hi"][i]
+        return A
+
+    def _ho_apply(self, op, lay, bc, x):
+        A = self._ho_matrix(op, lay.n, bc == 1)
+        out = np.zeros_like(x)
+        for ax in range(x.ndim):
+            out += np.moveaxis(np.tensordot(A, x, axes=([1], [ax])), 0, ax)
+        return out
+
+    def heat_eval_f_ho(self, lay, bc, op, us, fs, profile=None, gts=None, fexpls=None):
+        self.launches += 1
+        for i, (u, f) in enumerate(zip(us, fs)):
+            self._grid(lay, f)[...] = self._ho_apply(op, lay, bc, self._grid(lay, u))
+            if profile is not None:
+                self._grid(lay, fexpls[i])[...] = self._grid(lay, profile) * gts[i]
+
+    def cg_ho_workspace(self, lay, B):
+        return None
+
+    def heat_cg_solve_ho(self, lay, bc, op, factors, rhs, xs, rtol, maxiter, work, iters_dev):
+        self.launches += 1
+        for b, (r, x) in enumerate(zip(rhs, xs)):
+            mv = lambda v, fac=factors[b]: v - fac * self._ho_apply(op, lay, bc, v)  # noqa: E731
+            iters_dev[b] += self._cg(mv, self._grid(lay, r), self._grid(lay, x), rtol, maxiter)
+
     def heat_cg_solve_slab(self, lay, comm, bc, m_diag, m_off, rhs, xs, rtol, maxiter, work, iters_dev, precond=0):
         """Distributed CG with the same structure as the device solver: halo exchange of the search direction, global
         dot products through the communicator; the halo planes of xs are valid on entry."""
