@@ -86,11 +86,46 @@ __device__ __forceinline__ double2 node_value(const SweepArgs& a, int j, long lo
     return v;
 }
 
-template <int NOUT, int NCOMP>
+// SQUARE: as many input nodes as output nodes (the sweep's M x M combinations) - the trip counts are compile-time
+// constants, the loops unroll completely and all M*NCOMP loads of a point are in flight together; otherwise (node
+// additions with j <= m inputs, end point with one output) the generic loops run.
+template <int NOUT, int NCOMP, bool SQUARE>
 __device__ __forceinline__ void sweep_terms(const SweepArgs& a, long long i, double2 (&acc)[NOUT]) {
+    const int nj = SQUARE ? NOUT : a.nj;
+    if (SQUARE) {
+        double2 v[NOUT * NCOMP];
+#pragma unroll
+        for (int k = 0; k < NOUT * NCOMP; ++k) v[k] = ld2(a.in[k] + 2 * i);
+        if (a.flags & SDCB200_SWEEP_QUADRATURE) {
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+                double2 f = v[NCOMP * j];
+                if (NCOMP == 2) add2(f, v[2 * j + 1]);  // f[j].impl + f[j].expl  (imex_1st_order.py:53)
+#pragma unroll
+                for (int m = 0; m < NOUT; ++m) mul_add(acc[m], a.Wq[m * NOUT + j], f);
+            }
+        }
+        if (a.flags & SDCB200_SWEEP_QDELTA) {
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) {
+#pragma unroll
+                for (int m = 0; m < NOUT; ++m) {
+                    if (NCOMP == 1) {
+                        mul_add(acc[m], a.Wi[m * NOUT + j], v[j]);
+                    } else {
+                        double2 t;
+                        t.x = __dadd_rn(__dmul_rn(a.Wi[m * NOUT + j], v[2 * j].x), __dmul_rn(a.We[m * NOUT + j], v[2 * j + 1].x));
+                        t.y = __dadd_rn(__dmul_rn(a.Wi[m * NOUT + j], v[2 * j].y), __dmul_rn(a.We[m * NOUT + j], v[2 * j + 1].y));
+                        mul_add(acc[m], a.dt2, t);
+                    }
+                }
+            }
+        }
+        return;
+    }
     if (a.flags & SDCB200_SWEEP_QUADRATURE) {
-#pragma unroll 2
-        for (int j = 0; j < a.nj; ++j) {
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
             const double2 v = node_value<NCOMP>(a, j, i);
 #pragma unroll
             for (int m = 0; m < NOUT; ++m) mul_add(acc[m], a.Wq[m * a.nj + j], v);
@@ -117,7 +152,7 @@ __device__ __forceinline__ void sweep_terms(const SweepArgs& a, long long i, dou
     }
 }
 
-template <int NOUT, int NCOMP>
+template <int NOUT, int NCOMP, bool SQUARE>
 __global__ void __launch_bounds__(kThreads) colloc_sweep_kernel(const __grid_constant__ SweepArgs a) {
     const long long stride = (long long)gridDim.x * kThreads;
     const bool base_first = a.flags & SDCB200_SWEEP_BASE_FIRST;
@@ -127,7 +162,7 @@ __global__ void __launch_bounds__(kThreads) colloc_sweep_kernel(const __grid_con
         if (a.base != nullptr) b = ld2(a.base + 2 * i);
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) acc[m] = base_first ? b : make_double2(0.0, 0.0);
-        sweep_terms<NOUT, NCOMP>(a, i, acc);
+        sweep_terms<NOUT, NCOMP, SQUARE>(a, i, acc);
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) {
             if (!base_first && a.base != nullptr) add2(acc[m], b);
@@ -138,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) colloc_sweep_kernel(const __grid_con
 }
 
 // res[m] = sum_j (dt*Q[m][j]) f[j] + (u0 - u[m]) + tau[m];  resnorm[m] = max |res[m]|   (core/sweeper.py:186-195)
-template <int NOUT, int NCOMP>
+template <int NOUT, int NCOMP, bool SQUARE>
 __global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_constant__ SweepArgs a) {
     __shared__ double scratch[33];
     double vmax[NOUT];
@@ -150,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_
         double2 acc[NOUT];
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) acc[m] = make_double2(0.0, 0.0);
-        sweep_terms<NOUT, NCOMP>(a, i, acc);
+        sweep_terms<NOUT, NCOMP, SQUARE>(a, i, acc);
         const double2 u0 = ld2(a.base + 2 * i);
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) {
@@ -352,10 +387,13 @@ int sdcb200_colloc_sweep(long long count, int nout, int nj, int ncomp, int flags
     if (count == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int grid = stream_grid(a.count2);
-    switch (nout * 2 + (ncomp - 1)) {
+    const bool square = nj == nout && nout <= 4;  // (larger M: the register-resident variant would spill)
+    switch (nout * 4 + (ncomp - 1) * 2 + (square ? 1 : 0)) {
 #define CASE(N) \
-    case 2 * N: colloc_sweep_kernel<N, 1><<<grid, kThreads, 0, s>>>(a); break; \
-    case 2 * N + 1: colloc_sweep_kernel<N, 2><<<grid, kThreads, 0, s>>>(a); break;
+    case 4 * N: colloc_sweep_kernel<N, 1, false><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 1: colloc_sweep_kernel<N, 1, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 2: colloc_sweep_kernel<N, 2, false><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 3: colloc_sweep_kernel<N, 2, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
@@ -381,10 +419,13 @@ int sdcb200_colloc_residual(long long count, int M, int nj, int ncomp, const dou
     SDC_CUDA_OK(cudaMemsetAsync(resnorm_dev, 0, sizeof(double) * M, s));
     if (count == 0) return 0;
     const int grid = stream_grid(a.count2);
-    switch (M * 2 + (ncomp - 1)) {
+    const bool square = nj == M && M <= 4;
+    switch (M * 4 + (ncomp - 1) * 2 + (square ? 1 : 0)) {
 #define CASE(N) \
-    case 2 * N: colloc_residual_kernel<N, 1><<<grid, kThreads, 0, s>>>(a); break; \
-    case 2 * N + 1: colloc_residual_kernel<N, 2><<<grid, kThreads, 0, s>>>(a); break;
+    case 4 * N: colloc_residual_kernel<N, 1, false><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 1: colloc_residual_kernel<N, 1, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 2: colloc_residual_kernel<N, 2, false><<<grid, kThreads, 0, s>>>(a); break; \
+    case 4 * N + 3: colloc_residual_kernel<N, 2, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }

@@ -69,22 +69,22 @@ def main():
                       abs(float(np.max(np.abs(mine))) - float(g["uend_maxnorm"])) / float(g["uend_maxnorm"]))
         ref = g["niter"].tolist()
         note = ""
-        if got != ref and "residuals" in g:
-            # Full-size run: SDC stagnates at the accuracy the inner CG can attain (condition number ~1e5), so a
-            # stopping decision whose reference residual lies within 25 % of restol is decided by solver rounding
-            # noise.  Such slices may differ by one iteration; everything else must be identical.
-            restol = d["level_params"]["restol"]
-            ok_counts = True
-            for i, (a, b) in enumerate(zip(got, ref)):
-                if a == b:
-                    continue
-                r_ref = float(g["residuals"][i][min(a, b) - 1])
-                in_band = abs(a - b) == 1 and abs(r_ref - restol) <= 0.25 * restol
-                ok_counts = ok_counts and in_band
-                note += (f" [slice {i}: {a} vs {b} iterations, reference residual at iteration {min(a, b)} = {r_ref:.3e}"
-                         f" vs restol {restol:.0e}, ours {all_res[i][min(a, b) - 1]:.3e}]")
-        else:
-            ok_counts = got == ref
+        # Full-size run (BASELINE config 5): SDC stagnates at the accuracy the inner CG can attain, right at restol, and
+        # the UNMODIFIED reference does not hold its own count on such slices: oracle/sensitivity.py re-ran it with
+        # rounding-level perturbations of lintol / u0 and recorded where its count moves
+        # (tests/golden/sensitivity_config5.json).  Only on those slices may a count differ, by one.
+        import parity_cases as pc
+
+        loose = pc.sensitive_steps(name, ref)
+        ok_counts = len(got) == len(ref)
+        for i, (a, b) in enumerate(zip(got, ref)):
+            if a == b:
+                continue
+            ok_counts = ok_counts and i in loose and abs(a - b) == 1
+            r_ref = float(g["residuals"][i][min(a, b) - 1]) if "residuals" in g else float("nan")
+            note += (f" [slice {i}: {a} vs {b} iterations; the reference's residual at iteration {min(a, b)} is {r_ref:.3e}"
+                     f" vs restol {d['level_params']['restol']:.0e}, ours {all_res[i][min(a, b) - 1]:.3e}; reference "
+                     f"flips on this slice under rounding-level perturbations: {i in loose}]")
         ok = ok_counts and err < 1e-10
         nodes = c.S.levels[0].sweep.coll.num_nodes
         updates = P.dtype_u(P.init).size * nodes * sum(got)

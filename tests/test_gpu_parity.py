@@ -447,7 +447,8 @@ def test_slab_decomposed_run_on_two_gpus():
     assert "slab_check n=63 world=2: OK" in res.stdout
 
 
-@pytest.mark.parametrize("name,world", [("pfasst_heat2d_imex_63_p4", 4), ("pfasst_step8A_heat1d", 8)])
+@pytest.mark.parametrize("name,world", [("pfasst_heat2d_imex_63_p4", 4), ("pfasst_step8A_heat1d", 8),
+                                        ("pfasst_config5_1023_p8", 8)])  # the last one: BASELINE config 5 at full size
 def test_pfasst_time_slices(name, world):
     """PFASST with one process per time slice on the real kernels vs the reference's fixtures.  With enough GPUs the
     slices run one per GPU over NCCL; on a single-GPU box they share the device and hand over through gloo."""
@@ -463,3 +464,7 @@ def test_pfasst_time_slices(name, world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert ": OK" in res.stdout
+
+
+def test_spatial_accuracy_of_the_higher_order_stencils():
+    pc.check_spatial_accuracy(pmax=11)

@@ -171,3 +171,7 @@ def test_output_file_of_device_fields(tmp_path):
     assert RectilinearFile.fromFile(Log.filename).nFields == 5
     with pytest.raises(FileExistsError):
         P.getOutputFile(Log.filename)
+
+
+def test_spatial_accuracy_of_the_higher_order_stencils():
+    pc.check_spatial_accuracy(pmax=7)
