@@ -464,6 +464,10 @@ def run_b200(args):
     # ---- device-resident timing -------------------------------------------------------------------------------------
     for lvl in levels:
         lvl.prob.solve_log = []
+    tl_buf = None
+    if args.timeline:
+        tl_buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+        be.set_timeline(tl_buf)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -477,6 +481,13 @@ def run_b200(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = be.launches - launches0
+    timeline = None
+    if tl_buf is not None:
+        be.set_timeline(None)
+        t8 = (tl_buf.cpu().numpy() * 1e-6 / args.steps).tolist()  # ms per step
+        keys = ("work_between_syncs_ms", "grid_barrier_wait_ms", "partial_sums_ms", "cross_rank_exchange_ms")
+        timeline = dict(note="per step, %globaltimer inside the pipelined CG kernel (rank 0)",
+                        first_cta=dict(zip(keys, t8[:4])), last_cta=dict(zip(keys, t8[4:])))
     clocks = sampler.stop() if rank == 0 else None
     fine_log = list(L.prob.solve_log)
     coarse_log = [e for lvl in levels[1:] for e in lvl.prob.solve_log]
@@ -638,6 +649,8 @@ def run_b200(args):
                                   ms_per_launch=k_ms / max(n_launch, 1), share_of_step=k_ms / ms),
                     other_kernels={k: dict(v, frac_of_peak=v["achieved_gbs"] / peak) for k, v in other.items()},
                     clocks=clocks)
+        if timeline is not None:
+            line["timeline"] = timeline
         if b_alg is not None:
             line["roofline"]["whole_step_achieved"] = b_alg * updates_per_step * args.steps / (ms * 1e-3) / 1e9
         line["check"] = check_answer(w, world, residuals, niter, uend_maxabs, write=args.write_record)
@@ -672,6 +685,8 @@ def main():
     ap.add_argument("--no-reference-controller", action="store_true",
                     help="e2e leg through the stand-alone controller even when oracle/_ref is present")
     ap.add_argument("--precond", action="store_true", help="node solves with the polynomial preconditioner")
+    ap.add_argument("--timeline", action="store_true",
+                    help="add where the time inside the pipelined CG kernel goes (work / barrier / sums / cross-rank exchange)")
     ap.add_argument("--write-record", action="store_true", help="(re)write the committed answer record of this workload")
     args = ap.parse_args()
     if args.impl == "reference":

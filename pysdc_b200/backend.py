@@ -42,6 +42,7 @@ def _declare(lib):
         "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
         "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "sdcb200_set_timeline": (c_int, [_c_dp]),
         "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, _c_dp, c_sz, _c_dp,
                                           _c_dp]),
         "sdcb200_peer_alloc": (c_int, [c_sz, PP, ctypes.c_char_p]),
@@ -189,6 +190,10 @@ class CudaBackend:
                                                       _ptr_array(us), _ptr_array(fs), self._stream()))
 
     # -- K3 / K4 ------------------------------------------------------------------------------------------------------
+    def set_timeline(self, buf):
+        """buf: 8-element int64 device tensor the pipelined CG kernels add their phase timings to (None: off)."""
+        self._check(self.lib.sdcb200_set_timeline(None if buf is None else buf.data_ptr()))
+
     def cg_workspace(self, lay, B):
         nbytes = self.lib.sdcb200_cg_workspace_bytes(lay.ndim, lay.n, B)
         return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)

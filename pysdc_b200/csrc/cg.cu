@@ -189,17 +189,35 @@ __global__ void __launch_bounds__(kThreads) cg_kernel(const __grid_constant__ Cg
 // ---------------------------------------------------------------------------------------------------------------------
 // Sum the per-CTA partials of the listed (slot, system) pairs over the grid - and, on slab runs, over all ranks -
 // leaving the results in sh.glob[i] (bit-identical on every thread of every CTA of every rank).
+// `tl` (optional): ns accumulators of the first and the last CTA - [0] work since the previous synchronisation (the
+// pass itself, pipeline fill / drain, scalar updates), [1] wait in the grid barrier, [2] summing the partials,
+// [3] cross-rank exchange of the sums (slab runs).
 template <bool SLAB>
 __device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgShared& sh, const SlabLink* link,
-                                           unsigned long long& seq, const int* slots, const int* systems, int nv) {
+                                           unsigned long long& seq, const int* slots, const int* systems, int nv,
+                                           unsigned long long* tl = nullptr) {
+    const bool rec = tl != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    unsigned long long t0 = 0, t1 = 0, t2 = 0;
+    if (rec) t0 = global_ns();
     if (SLAB) grid_barrier_sys(bar);
     else grid_barrier(bar);
+    if (rec) t1 = global_ns();
     for (int i = 0; i < nv; ++i) {
         const double v = grid_sum(partials, slots[i], systems[i], sh.scratch);
         if (threadIdx.x == 0) (SLAB ? sh.loc : sh.glob)[i] = v;
     }
+    if (rec) t2 = global_ns();
     if (SLAB) cross_rank_sum(*link, sh, nv, ++seq);
     else __syncthreads();
+    if (rec) {
+        const unsigned long long t3 = global_ns();
+        unsigned long long* a = tl + (blockIdx.x == 0 ? 0 : 4);
+        a[0] += t0 - sh.t_last;
+        a[1] += t1 - t0;
+        a[2] += t2 - t1;
+        a[3] += t3 - t2;
+        sh.t_last = t3;
+    }
 }
 
 // All threads of the grid (and, on slabs, of all ranks) call this with identical arguments.  `start_mask`: the systems
@@ -207,7 +225,8 @@ __device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgSh
 template <int NDIM, bool SLAB, bool PER, bool DIAG, class SMEM>
 __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, const Sys* s, const PipeMaps& maps,
                                    int maxiter, double* partials, unsigned* bar, CgShared& sh, SMEM& sm,
-                                   const SlabLink* link, unsigned& kstep) {
+                                   const SlabLink* link, unsigned& kstep, unsigned long long* tl = nullptr) {
+    if (threadIdx.x == 0) sh.t_last = global_ns();
     const Units U = make_units(g, (int)gridDim.x);
     const PUnits PU = make_punits(g, 1, (int)gridDim.x);
     const long long n2 = g.owned / 2;
@@ -264,7 +283,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
     }
     __syncthreads();
     fence_proxy_async_global();
-    reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, r_count);
+    reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, r_count, tl);
     if (threadIdx.x == 0) {
         unsigned act = 0;
         for (int i = 0; i < r_count; i += 2) {
@@ -307,7 +326,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
             pa.slot = kSlotC;
             pipe_pass<NDIM, PER, DIAG, kPhaseC>(g, PU, s, maps, sh, sm, partials, kstep, pa);
             fence_proxy_async_global();
-            reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc);
+            reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc, tl);
             if ((int)threadIdx.x < nc) sh.rz[r_sys[threadIdx.x]] = sh.glob[threadIdx.x];
             __syncthreads();
         }
@@ -348,7 +367,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
         pipe_pass<NDIM, PER, DIAG, kPhaseA>(g, PU, s, maps, sh, sm, partials, kstep, pa);
         if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotA;
         fence_proxy_async_global();
-        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
+        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact, tl);
         if ((int)threadIdx.x < nact) sh.alpha[r_sys[threadIdx.x]] = sh.rz[r_sys[threadIdx.x]] / sh.glob[threadIdx.x];
         __syncthreads();
 
@@ -358,7 +377,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
         pipe_pass<NDIM, PER, DIAG, kPhaseB>(g, PU, s, maps, sh, sm, partials, kstep, pa);
         if (threadIdx.x < nact) r_slots[threadIdx.x] = kSlotB;
         fence_proxy_async_global();
-        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact);
+        reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nact, tl);
         if ((int)threadIdx.x < nact) {
             const int b = r_sys[threadIdx.x];
             sh.rr[b] = sh.glob[threadIdx.x];
@@ -392,7 +411,7 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
                 pa.slot = kSlotC;
                 pipe_pass<NDIM, PER, DIAG, kPhaseC>(g, PU, s, maps, sh, sm, partials, kstep, pa);
                 fence_proxy_async_global();
-                reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc);
+                reduce_all<SLAB>(partials, bar, sh, link, seq, r_slots, r_sys, nc, tl);
                 if ((int)threadIdx.x < nc) {
                     const int b = r_sys[threadIdx.x];
                     sh.rho_prev[b] = sh.rz[b];
@@ -423,7 +442,7 @@ __global__ void __maxnreg__(112) cg_pipe_kernel(const __grid_constant__ PipeArgs
     __syncthreads();
     unsigned kstep = 0;
     cg_collective_pipe<NDIM, SLAB, PER, false>(a.g, a.B, (1u << a.B) - 1u, a.s, pa.maps, a.maxiter, a.partials, a.bar, sh,
-                                                sm, SLAB ? &pa.link : nullptr, kstep);
+                                                sm, SLAB ? &pa.link : nullptr, kstep, a.timeline);
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.iters_out != nullptr)
         for (int b = 0; b < a.B; ++b) a.iters_out[b] += sh.iters[b];
 }
@@ -578,6 +597,7 @@ int coresident_ctas(K kernel, int* out) {
 }
 
 constexpr int kMaxGrid = 148 * 8;  // upper bound used to size the partials area
+unsigned long long* g_timeline = nullptr;  // sdcb200_set_timeline
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -646,6 +666,7 @@ int launch_cg_pipe(CgArgs& cg, cudaStream_t s, const SlabLink* link = nullptr) {
     if (grid > kMaxGrid) grid = kMaxGrid;
     static thread_local PipeArgs a;  // ~16 KB: kept off the stack
     a.cg = cg;
+    a.cg.timeline = g_timeline;
     if (link != nullptr) a.link = *link;
     for (int b = 0; b < cg.B; ++b)
         if (int rc = encode_system_maps(a.maps.m[b], cg.g, cg.s[b])) return rc;
@@ -681,6 +702,11 @@ int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas)
     if (solver_ctas) {
         if (int rc = pipe_grid<cg_pipe_kernel<3, false, false>>(sizeof(PipeSmemT<false, false>), solver_ctas)) return rc;
     }
+    return 0;
+}
+
+int sdcb200_set_timeline(unsigned long long* dev_ns8) {
+    g_timeline = dev_ns8;
     return 0;
 }
 

@@ -27,6 +27,7 @@ struct CgArgs {
     double* partials;  // [2][MAX_NODES][gridDim.x]
     unsigned* bar;     // grid barrier word (zero before the launch)
     int* iters_out;    // [B], += iterations
+    unsigned long long* timeline;  // optional [2][4] ns accumulators (sdcb200_set_timeline): where the time of a solve goes
 };
 
 // Batched Allen-Cahn Newton solves: system b solves  u - factor_b (A u + 1/eps^2 u (1 - u^nu)) = rhs_b  for u_b.  The
@@ -147,6 +148,7 @@ struct CgShared {
     double rtol[SDCB200_MAX_NODES];  // relative tolerance of each system (set by the caller of the collective solver)
     int iters[SDCB200_MAX_NODES];
     unsigned active;  // bit b set: system b still iterating
+    unsigned long long t_last;  // timeline: end of the previous synchronisation
 };
 
 // Cross-rank sum of `nv` values per rank (sh.loc[0..nv) on entry, identical in every CTA of the rank).  On return
