@@ -799,6 +799,15 @@ int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const d
     L.nranks = nranks;
     L.has_lo = rank > 0;
     L.has_hi = rank + 1 < nranks;
+    // Ranks launch their solver kernels without host synchronisation: a peer may legitimately be late (host stall, GC,
+    // a debugger).  Default 300 s; the trap that follows a time-out kills this rank's context, which the host sees as a
+    // CUDA error at its next call instead of a GPU that spins forever.
+    {
+        const char* env = getenv("SDCB200_PEER_TIMEOUT_S");
+        double secs = env != nullptr ? atof(env) : 300.0;
+        if (!(secs > 0.0)) secs = 300.0;
+        L.timeout_ns = (unsigned long long)(secs * 1e9);
+    }
     L.seq = reinterpret_cast<unsigned long long*>(base + w.seq_off);
     L.error = reinterpret_cast<int*>(base + w.err_off);
     for (int r = 0; r < nranks; ++r) {

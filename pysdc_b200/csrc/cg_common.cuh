@@ -113,6 +113,7 @@ struct SlabLink {
     double* vals_of[kMaxRanks];                  // [2][kMaxRanks][kMailVals]
     unsigned long long* seq;                     // own persistent synchronisation counter
     int* error;                                  // own: set to 1 when a peer did not show up in time
+    unsigned long long timeout_ns;               // how long to wait for a peer before giving up (SDCB200_PEER_TIMEOUT_S)
 };
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -175,7 +176,7 @@ __device__ __forceinline__ void cross_rank_sum(const SlabLink& L, CgShared& sh, 
             if ((++spins & 0x3ffu) == 0) {
                 const unsigned long long now = global_ns();
                 if (t0 == 0) t0 = now;
-                else if (now - t0 > 20000000000ull) {  // 20 s without the peer: give up loudly instead of hanging the GPU
+                else if (now - t0 > L.timeout_ns) {  // the peer never showed up: give up loudly instead of hanging the GPU
                     *L.error = 1;
                     __threadfence_system();
                     __trap();

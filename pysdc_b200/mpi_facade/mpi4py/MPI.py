@@ -1,8 +1,9 @@
 """``mpi4py.MPI`` facade: constants, ``Intracomm`` and request objects backed by ``pysdc_b200.parallel.TorchComm``.
 
-Messages between a pair of ranks are matched in order (NCCL / gloo point-to-point semantics); tags are accepted and
-ignored, which is sufficient because both ends of pySDC's time-parallel controller issue their sends and receives in
-the same deterministic stage order (controller_MPI.py:218-305).  Numpy buffers (``[array, MPI.DOUBLE]``) travel as
+Messages between a pair of ranks are matched in order (NCCL / gloo point-to-point semantics), not by tag, which is
+sufficient because both ends of pySDC's time-parallel controller issue their sends and receives in the same
+deterministic stage order (controller_MPI.py:218-305); with SDCB200_CHECK_TAGS=1 the tags of the field messages travel
+in a header and a mismatch raises (the multi-process tests run that way).  Numpy buffers (``[array, MPI.DOUBLE]``) travel as
 small tensors, Python objects through the object collectives."""
 import numpy as np
 import torch
@@ -63,6 +64,9 @@ class Intracomm:
 
     def Split(self, color=0, key=0):
         """Sub-communicator of the ranks that passed the same ``color`` (bool or int), ordered by rank."""
+        if self.tc.group is not None:
+            # torch.distributed.new_group is collective over the DEFAULT group (see parallel.TorchComm.first)
+            raise NotImplementedError("Split is implemented for the world communicator only")
         colors = self.tc.allgather(int(color))
         mine = None
         for c in sorted(set(colors)):  # every rank creates every group, in the same order
@@ -114,6 +118,8 @@ class Intracomm:
         return Request([dist.irecv(t, self.tc._global(source), group=self.tc.group)], after=fill, keep=t)
 
     def Issend(self, buf, dest=0, tag=0):
+        if hasattr(buf, "_buf") or torch.is_tensor(buf):
+            return self._track(self.tc.Issend(buf, dest=dest, tag=tag))
         return self._send_buffer(buf, dest)
 
     Isend = Issend
@@ -122,6 +128,8 @@ class Intracomm:
         self._send_buffer(buf, dest).Wait()
 
     def Irecv(self, buf, source=0, tag=0):
+        if hasattr(buf, "_buf") or torch.is_tensor(buf):
+            return self.tc.Irecv(buf, source=source, tag=tag)
         return self._recv_buffer(buf, source)
 
     def Recv(self, buf, source=0, tag=0):

@@ -13,6 +13,8 @@ is NCCL over NVLink (``torch.distributed``, backend ``nccl``; ``gloo`` with CPU 
   the registry of peer-mapped solver workspaces (``backend.slab_cg_workspace``).  Passing it as ``comm=`` to the heat
   problem classes turns their fields into slabs.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -109,6 +111,10 @@ class TorchComm:
         first time a given count is requested (torch.distributed.new_group must be entered by every rank)."""
         if count == self.size:
             return self
+        if self.group is not None:
+            # torch.distributed.new_group is collective over the DEFAULT group: a communicator that is itself a
+            # sub-group (time x space splittings) cannot create further groups without the ranks outside it
+            raise NotImplementedError("sub-communicators can only be created from the world communicator")
         if count not in self._subgroups:
             ranks = [self._global(r) for r in range(count)]
             g = dist.new_group(ranks=ranks)
@@ -171,21 +177,49 @@ class TorchComm:
     def _storage(field):
         return field._buf if hasattr(field, "_buf") else field
 
+    # Messages between two ranks are matched in ORDER (NCCL / gloo semantics), not by tag.  That is sufficient while both
+    # ends post their sends and receives in the same order (pySDC's controllers do: controller_MPI.py:218-305).  With
+    # SDCB200_CHECK_TAGS=1 every field message is preceded by a one-element header carrying the tag and the receiver
+    # raises on a mismatch - the multi-process tests run that way.
+    _check_tags = os.environ.get("SDCB200_CHECK_TAGS", "0") == "1"
+
+    def _tag_header(self, tag):
+        dev = torch.device("cpu") if self._host_staged else self.device
+        return torch.tensor([-1 if tag is None else int(tag)], dtype=torch.int64, device=dev)
+
     def Issend(self, field, dest=None, tag=None):
         t = self._storage(field)
+        head, works = None, []
+        if self._check_tags:
+            head = self._tag_header(tag)
+            works.append(dist.isend(head, self._global(dest), group=self.group))
         if self._host_staged and t.is_cuda:
             h = t.cpu()
-            return Request([dist.isend(h, self._global(dest), group=self.group)], keep=h)
-        return Request([dist.isend(t, self._global(dest), group=self.group)])
+            return Request(works + [dist.isend(h, self._global(dest), group=self.group)], keep=(h, head))
+        return Request(works + [dist.isend(t, self._global(dest), group=self.group)], keep=head)
 
     Isend = Issend
 
     def Irecv(self, field, source=None, tag=None):
         t = self._storage(field)
+        head, works, check = None, [], None
+        if self._check_tags:
+            head = self._tag_header(None)
+            works.append(dist.irecv(head, self._global(source), group=self.group))
+
+            def check():
+                got = int(head.item())
+                if tag is not None and got != -1 and got != int(tag):
+                    raise RuntimeError(f"message order mismatch: expected tag {tag} from rank {source}, got {got}")
         if self._host_staged and t.is_cuda:
             h = torch.empty(t.shape, dtype=t.dtype)
-            return Request([dist.irecv(h, self._global(source), group=self.group)], after=lambda: t.copy_(h), keep=h)
-        return Request([dist.irecv(t, self._global(source), group=self.group)])
+
+            def after():
+                if check is not None:
+                    check()
+                t.copy_(h)
+            return Request(works + [dist.irecv(h, self._global(source), group=self.group)], after=after, keep=(h, head))
+        return Request(works + [dist.irecv(t, self._global(source), group=self.group)], after=check, keep=head)
 
     def Send(self, field, dest=None, tag=None):
         self.Issend(field, dest, tag).Wait()

@@ -262,7 +262,10 @@ class HeatMixin(OutputMixin):
             if self._ho is not None:
                 self._work[B] = self._be.cg_ho_workspace(self._lay, B)
             elif self._comm is not None:
+                import weakref
+
                 self._work[B] = self._be.slab_cg_workspace(self._lay, self._comm, B)
+                weakref.finalize(self, self._work[B].close)  # unmap the peers' segments, free our own
             else:
                 self._work[B] = self._be.cg_workspace(self._lay, B)
         return self._work[B]
