@@ -68,21 +68,24 @@ enum PipePhase { kPhaseA = 0, kPhaseB = 1, kPhaseC = 2, kPhaseF = 3 };
 
 // Shared-memory geometry of one kernel variant.  A stage holds up to two boxes with halo (+ their wrap sets on periodic
 // grids) and up to three (four with a diagonal) tile-only boxes; it is sized for the largest phase of the variant.
-template <bool PER, bool DIAG>
+// EVAL: the variant of the eval_f kernel - one box with halo and one tile-only box per stage, so the pipeline can be
+// deeper (its single 10 KB box per step needs more steps in flight than the solver's 20-36 KB stages to keep HBM busy).
+template <bool PER, bool DIAG, bool EVAL = false>
 struct PipeCfg {
     static constexpr int kWrap = PER ? kWrapSetBytes : 0;
     static constexpr int kBytesA = 2 * kHaloSlot + 2 * kWrap + (DIAG ? kCentreBoxBytes : 0);
     static constexpr int kBytesB = kHaloSlot + kWrap + (2 + (DIAG ? 1 : 0)) * kCentreBoxBytes;
-    static constexpr int kStageBytes = (kBytesA > kBytesB ? kBytesA : kBytesB);
+    static constexpr int kBytesF = kHaloSlot + kWrap + kCentreBoxBytes;
+    static constexpr int kStageBytes = EVAL ? kBytesF : (kBytesA > kBytesB ? kBytesA : kBytesB);
     // 2 CTAs per SM must fit into 227 KB together with the static shared memory of the solver
-    static constexpr int kStages = (PER || DIAG) ? 3 : 4;
+    static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
     // offsets inside a stage
     __host__ __device__ static constexpr int halo_off(int f) { return f * (kHaloSlot + kWrap); }
     __host__ __device__ static constexpr int wrap_off(int f) { return f * (kHaloSlot + kWrap) + kHaloSlot; }
     __host__ __device__ static constexpr int centre_off(int nh, int f) { return nh * (kHaloSlot + kWrap) + f * kCentreBoxBytes; }
 };
 
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 5;
 struct PipeCtl {
     unsigned long long full[kMaxStages];
     unsigned long long empty[kMaxStages];
@@ -90,9 +93,10 @@ struct PipeCtl {
     int act_list[SDCB200_MAX_NODES];
     int nact;
 };
-template <bool PER, bool DIAG>
+template <bool PER, bool DIAG, bool EVAL = false>
 struct PipeSmemT {
-    alignas(128) unsigned char st[PipeCfg<PER, DIAG>::kStages][PipeCfg<PER, DIAG>::kStageBytes];
+    using Cfg = PipeCfg<PER, DIAG, EVAL>;
+    alignas(128) unsigned char st[Cfg::kStages][Cfg::kStageBytes];
     PipeCtl ctl;
 };
 
@@ -312,7 +316,7 @@ struct PassArgs {
 template <int NDIM, bool PER, bool DIAG, int PHASE, class SMEM>
 __device__ void pipe_pass(const Geom& g, const PUnits& U, const Sys* s, const PipeMaps& maps, const CgShared& sh, SMEM& sm,
                           double* partials, unsigned& kstep, const PassArgs pa) {
-    using Cfg = PipeCfg<PER, DIAG>;
+    using Cfg = typename SMEM::Cfg;
     constexpr int kStages = Cfg::kStages;
     // boxes of a step of this phase
     constexpr int NH = PHASE == kPhaseA ? 2 : 1;                        // boxes with halo (A: r, p_old)

@@ -75,11 +75,11 @@ struct EvalPipeArgs {
 
 template <int NDIM, bool PER>
 __global__ void __maxnreg__(112) eval_pipe_kernel(const __grid_constant__ EvalPipeArgs a) {
-    using Smem = PipeSmemT<PER, false>;
+    using Smem = PipeSmemT<PER, false, true>;
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
     __shared__ CgShared sh;  // not used by this phase (no reductions)
-    pipe_ctl_init(sm.ctl, PipeCfg<PER, false>::kStages);
+    pipe_ctl_init(sm.ctl, Smem::Cfg::kStages);
     if (threadIdx.x == 0) {
         sm.ctl.nact = a.B;
         for (int b = 0; b < a.B; ++b) sm.ctl.act_list[b] = b;
@@ -95,7 +95,7 @@ __global__ void __maxnreg__(112) eval_pipe_kernel(const __grid_constant__ EvalPi
 template <int NDIM, bool PER>
 int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
     static thread_local EvalPipeArgs a;
-    const size_t smem = sizeof(PipeSmemT<PER, false>);
+    const size_t smem = sizeof(PipeSmemT<PER, false, true>);
     int ctas = 0;
     if (int rc = pipe_grid<eval_pipe_kernel<NDIM, PER>>(smem, &ctas)) return rc;
     for (int b0 = 0; b0 < e.B; b0 += SDCB200_MAX_NODES) {  // at most MAX_NODES fields per launch (M + 1 fields in predict)
