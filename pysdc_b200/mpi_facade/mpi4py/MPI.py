@@ -64,9 +64,10 @@ class Intracomm:
 
     def Split(self, color=0, key=0):
         """Sub-communicator of the ranks that passed the same ``color`` (bool or int), ordered by rank."""
-        if self.tc.group is not None:
-            # torch.distributed.new_group is collective over the DEFAULT group (see parallel.TorchComm.first)
-            raise NotImplementedError("Split is implemented for the world communicator only")
+        if self.tc.size != dist.get_world_size():
+            # torch.distributed.new_group is collective over the DEFAULT group: every rank of the job has to enter it, so
+            # only a communicator that spans all of them can split (see parallel.TorchComm.first)
+            raise NotImplementedError("Split needs a communicator that spans all ranks of the job")
         colors = self.tc.allgather(int(color))
         mine = None
         for c in sorted(set(colors)):  # every rank creates every group, in the same order

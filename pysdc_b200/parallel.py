@@ -111,10 +111,10 @@ class TorchComm:
         first time a given count is requested (torch.distributed.new_group must be entered by every rank)."""
         if count == self.size:
             return self
-        if self.group is not None:
-            # torch.distributed.new_group is collective over the DEFAULT group: a communicator that is itself a
-            # sub-group (time x space splittings) cannot create further groups without the ranks outside it
-            raise NotImplementedError("sub-communicators can only be created from the world communicator")
+        if self.size != dist.get_world_size():
+            # torch.distributed.new_group is collective over the DEFAULT group: a communicator that covers only part of
+            # the job (time x space splittings) cannot create further groups without the ranks outside it
+            raise NotImplementedError("sub-communicators can only be created from a communicator that spans the job")
         if count not in self._subgroups:
             ranks = [self._global(r) for r in range(count)]
             g = dist.new_group(ranks=ranks)

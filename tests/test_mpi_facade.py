@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(REF_PATHS is None, reason="reference tree not pr
 
 
 def _worker(rank, world, port, name, out_dir, kind, ref_paths):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     for p in reversed(ref_paths):

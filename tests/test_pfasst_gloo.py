@@ -39,7 +39,7 @@ def _description(name):
 
 
 def _worker(rank, world, port, name, out_dir, Tend_override=None):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     dist.init_process_group("gloo", rank=rank, world_size=world)
