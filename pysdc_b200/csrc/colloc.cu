@@ -182,16 +182,20 @@ __global__ void __launch_bounds__(kThreads) colloc_residual_kernel(const __grid_
     for (int m = 0; m < NOUT; ++m) vmax[m] = 0.0;
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < a.count2; i += stride) {
+        // all loads of this point first (node values, u0, then the right-hand sides inside sweep_terms): 2M+1 (3M+1 for
+        // IMEX) independent 16-byte loads in flight per thread
+        double2 um[NOUT];
+#pragma unroll
+        for (int m = 0; m < NOUT; ++m) um[m] = ld2(a.u[m] + 2 * i);
+        const double2 u0 = ld2(a.base + 2 * i);
         double2 acc[NOUT];
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) acc[m] = make_double2(0.0, 0.0);
         sweep_terms<NOUT, NCOMP, SQUARE>(a, i, acc);
-        const double2 u0 = ld2(a.base + 2 * i);
 #pragma unroll
         for (int m = 0; m < NOUT; ++m) {
-            const double2 um = ld2(a.u[m] + 2 * i);
-            acc[m].x = __dadd_rn(acc[m].x, __dadd_rn(u0.x, -um.x));  // res += u[0] - u[m+1]  (sweeper.py:188)
-            acc[m].y = __dadd_rn(acc[m].y, __dadd_rn(u0.y, -um.y));
+            acc[m].x = __dadd_rn(acc[m].x, __dadd_rn(u0.x, -um[m].x));  // res += u[0] - u[m+1]  (sweeper.py:188)
+            acc[m].y = __dadd_rn(acc[m].y, __dadd_rn(u0.y, -um[m].y));
             if (a.add[m] != nullptr) add2(acc[m], ld2(a.add[m] + 2 * i));
             if (a.out[m] != nullptr) st2(a.out[m] + 2 * i, acc[m]);
             vmax[m] = fmax(vmax[m], fmax(fabs(acc[m].x), fabs(acc[m].y)));
@@ -419,7 +423,9 @@ int sdcb200_colloc_residual(long long count, int M, int nj, int ncomp, const dou
     SDC_CUDA_OK(cudaMemsetAsync(resnorm_dev, 0, sizeof(double) * M, s));
     if (count == 0) return 0;
     const int grid = stream_grid(a.count2);
-    const bool square = nj == M && M <= 4;
+    // (the register-resident variant pays off for the sweep kernel only: with the node values and the norms on top it
+    // needs 120 registers and was measured at half the bandwidth of the generic loops)
+    const bool square = false;
     switch (M * 4 + (ncomp - 1) * 2 + (square ? 1 : 0)) {
 #define CASE(N) \
     case 4 * N: colloc_residual_kernel<N, 1, false><<<grid, kThreads, 0, s>>>(a); break; \
