@@ -500,8 +500,27 @@ def run_b200(args):
         lvl.prob.solve_log = []
     tl_buf = None
     if args.timeline:
-        tl_buf = torch.zeros(8, dtype=torch.int64, device="cuda")
+        tl_buf = torch.zeros(12, dtype=torch.int64, device="cuda")
         be.set_timeline(tl_buf)
+        # host-side view of the same steps: CUDA-event time of the stages around the solver (halo exchange of the
+        # initial guesses / of u before eval_f, collocation kernels, eval_f, the residual read)
+        stage_ev = {}
+
+        def timed_stage(name, fn):
+            def wrapped(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **k)
+                e1.record()
+                stage_ev.setdefault(name, []).append((e0, e1))
+                return out
+            return wrapped
+
+        for name in ("colloc_sweep", "colloc_residual", "heat_eval_f", "heat_cg_solve", "heat_cg_solve_slab"):
+            setattr(be, name, timed_stage(name, getattr(be, name)))
+        if comm is not None:
+            comm.exchange_halos = timed_stage("halo_exchange_nccl", comm.exchange_halos)
+            comm.allreduce_device = timed_stage("residual_allreduce_nccl", comm.allreduce_device)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -518,10 +537,18 @@ def run_b200(args):
     timeline = None
     if tl_buf is not None:
         be.set_timeline(None)
-        t8 = (tl_buf.cpu().numpy() * 1e-6 / args.steps).tolist()  # ms per step
+        raw = tl_buf.cpu().numpy()
+        t8 = (raw[:8] * 1e-6 / args.steps).tolist()  # ms per step
         keys = ("work_between_syncs_ms", "grid_barrier_wait_ms", "partial_sums_ms", "cross_rank_exchange_ms")
-        timeline = dict(note="per step, %globaltimer inside the pipelined CG kernel (rank 0)",
-                        first_cta=dict(zip(keys, t8[:4])), last_cta=dict(zip(keys, t8[4:])))
+        torch.cuda.synchronize()
+        stages = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in stage_ev.items()}
+        for name in list(stage_ev):
+            stage_ev[name] = []
+        timeline = dict(note="per step, rank 0: %globaltimer inside the pipelined CG kernel (first / last CTA of the grid) "
+                             "and CUDA-event time of the host-visible stages",
+                        first_cta=dict(zip(keys, t8[:4])), last_cta=dict(zip(keys, t8[4:8])),
+                        launch_shape=dict(ctas=int(raw[8]), units_per_system=int(raw[9]), planes_per_unit=int(raw[10])),
+                        stages_ms=stages)
     clocks = sampler.stop() if rank == 0 else None
     fine_log = list(L.prob.solve_log)
     coarse_log = [e for lvl in levels[1:] for e in lvl.prob.solve_log]

@@ -129,8 +129,9 @@ size_t sdcb200_cg_workspace_bytes(int ndim, int n, int B);
 /* Measurement aid (bench.py --timeline): dev_ns8 != NULL makes the pipelined CG kernels of the calling thread's later
  * launches add, in nanoseconds of %globaltimer, for the first CTA ([0..3]) and the last CTA ([4..7]) of the grid: [0] time
  * spent working between synchronisations (passes incl. pipeline fill / drain and tail), [1] waiting in the grid barrier,
- * [2] summing the partials, [3] in the cross-rank exchange of the sums (slab runs).  NULL switches it off.            */
-int sdcb200_set_timeline(unsigned long long* dev_ns8);
+ * [2] summing the partials, [3] in the cross-rank exchange of the sums (slab runs); [8..10] = grid size, units per system, planes per unit of
+ * the last launch.  The buffer holds 12 values.  NULL switches it off.                                               */
+int sdcb200_set_timeline(unsigned long long* dev_ns12);
 int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
                           const double* const* rhs, double* const* x, double rtol, int maxiter, int precond,
                           void* work, size_t work_bytes, int* iters_dev, void* stream);

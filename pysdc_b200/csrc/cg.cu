@@ -227,6 +227,12 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
                                    int maxiter, double* partials, unsigned* bar, CgShared& sh, SMEM& sm,
                                    const SlabLink* link, unsigned& kstep, unsigned long long* tl = nullptr) {
     if (threadIdx.x == 0) sh.t_last = global_ns();
+    if (tl != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {  // the launch shape the timings belong to
+        const PUnits pu = make_punits(g, 1, (int)gridDim.x);
+        tl[8] = gridDim.x;
+        tl[9] = (unsigned long long)pu.per_field;
+        tl[10] = (unsigned long long)pu.chunk_z;
+    }
     const Units U = make_units(g, (int)gridDim.x);
     const PUnits PU = make_punits(g, 1, (int)gridDim.x);
     const long long n2 = g.owned / 2;
@@ -705,8 +711,8 @@ int sdcb200_device_info(int* sm, int* cc_major, int* cc_minor, int* solver_ctas)
     return 0;
 }
 
-int sdcb200_set_timeline(unsigned long long* dev_ns8) {
-    g_timeline = dev_ns8;
+int sdcb200_set_timeline(unsigned long long* dev_ns12) {
+    g_timeline = dev_ns12;
     return 0;
 }
 
