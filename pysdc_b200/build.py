@@ -24,7 +24,8 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("SDCB200_NVCC_DEFS", "").split()  # e.g. -DSDCB200_TWO_CTAS (A/B experiments)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -430,6 +430,12 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
     if (SLAB && blockIdx.x == 0 && threadIdx.x == 0) *link->seq = seq;
 }
 
+#ifdef SDCB200_TWO_CTAS
+#define SDCB200_SOLVER_MAXNREG 96
+#else
+#define SDCB200_SOLVER_MAXNREG 128
+#endif
+
 struct PipeArgs {
     CgArgs cg;
     PipeMaps maps;
@@ -437,7 +443,7 @@ struct PipeArgs {
 };
 
 template <int NDIM, bool SLAB, bool PER>
-__global__ void __maxnreg__(112) cg_pipe_kernel(const __grid_constant__ PipeArgs pa) {
+__global__ void __maxnreg__(SDCB200_SOLVER_MAXNREG) cg_pipe_kernel(const __grid_constant__ PipeArgs pa) {
     using Smem = PipeSmemT<PER, false>;
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
@@ -474,7 +480,7 @@ struct NewtonPipeArgs {
     PipeMaps maps;
 };
 
-__global__ void __maxnreg__(112) newton_pipe_kernel(const __grid_constant__ NewtonPipeArgs npa) {
+__global__ void __maxnreg__(SDCB200_SOLVER_MAXNREG) newton_pipe_kernel(const __grid_constant__ NewtonPipeArgs npa) {
     using Smem = PipeSmemT<true, true>;
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
