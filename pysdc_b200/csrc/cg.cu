@@ -430,10 +430,10 @@ __device__ void cg_collective_pipe(const Geom& g, int B, unsigned start_mask, co
     if (SLAB && blockIdx.x == 0 && threadIdx.x == 0) *link->seq = seq;
 }
 
-#ifdef SDCB200_TWO_CTAS
-#define SDCB200_SOLVER_MAXNREG 96
-#else
+#ifdef SDCB200_ONE_CTA
 #define SDCB200_SOLVER_MAXNREG 128
+#else
+#define SDCB200_SOLVER_MAXNREG 96  // two CTAs per SM (see PipeCfg)
 #endif
 
 struct PipeArgs {

@@ -77,13 +77,14 @@ struct PipeCfg {
     static constexpr int kBytesB = kHaloSlot + kWrap + (2 + (DIAG ? 1 : 0)) * kCentreBoxBytes;
     static constexpr int kBytesF = kHaloSlot + kWrap + kCentreBoxBytes;
     static constexpr int kStageBytes = EVAL ? kBytesF : (kBytesA > kBytesB ? kBytesA : kBytesB);
-    // Solver kernels: ONE CTA per SM (their ~110 registers x 288 threads do not leave room for a second one: 5 warps on
-    // one SM sub-partition would need 5 x 112 x 32 > 16 K registers), so the pipeline takes the whole 227 KB: 8 / 6 stages
-    // = up to 180 KB of loads in flight per SM.  eval_f (93 registers): 2 CTAs per SM with 5 stages each.
-#ifdef SDCB200_TWO_CTAS  // A/B switch (scripts/gpu_r2i.sh): round-1 shape, 2 CTAs per SM with shallow pipelines
-    static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
-#else
+    // 2 CTAs per SM (16 consumer warps) must fit into 227 KB together with the static shared memory of the solver; the
+    // kernels are held to 96 registers for that (5 warps of one SM sub-partition x 96 x 32 <= 16 K registers).
+    // Measured alternative (-DSDCB200_ONE_CTA, profiles/r02/ab_one_vs_two_ctas.txt): ONE CTA per SM with 8 / 6 stages
+    // is 8-10 % slower on every configuration - the consumers, not the bytes in flight, are what a second CTA adds.
+#ifdef SDCB200_ONE_CTA
     static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 6 : 8);
+#else
+    static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
 #endif
     // offsets inside a stage
     __host__ __device__ static constexpr int halo_off(int f) { return f * (kHaloSlot + kWrap); }
