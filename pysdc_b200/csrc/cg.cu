@@ -562,7 +562,7 @@ __global__ void __maxnreg__(SDCB200_SOLVER_MAXNREG) newton_pipe_kernel(const __g
         grid_barrier(cg.bar);  // everybody has read the residual norms before anybody can come back and rewrite them
 
         cg_collective_pipe<2, false, true, true>(g, B, go, cg.s, npa.maps, a.lin_maxiter, cg.partials, cg.bar, sh, sm,
-                                                 nullptr, kstep);
+                                                 nullptr, kstep, cg.timeline);
         if ((int)threadIdx.x < B && (go >> threadIdx.x & 1u)) {
             s_linear[threadIdx.x] += sh.iters[threadIdx.x];
             s_newton[threadIdx.x] += 1;
@@ -912,6 +912,7 @@ int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, doub
     a.lin_maxiter = lin_maxiter;
     a.cg.partials = reinterpret_cast<double*>(base + w.partials_off);
     a.cg.bar = reinterpret_cast<unsigned*>(base + w.bar_off);
+    a.cg.timeline = g_timeline;
     a.counters_out = counters_dev;
     SDC_CUDA_OK(cudaMemsetAsync(a.cg.bar, 0, 256, s));
     int grid = 0;
