@@ -110,9 +110,10 @@ int sdcb200_heat_eval_f(int ndim, int n, int bc, double a_diag, double a_off, in
                         const double* const* u, double* const* f_impl,
                         const double* profile, const double* gt_host, double* const* f_expl, void* stream);
 
-/* f = A u + inv_eps2 * u * (1 - u^nu_exp)   (allencahn_fullyimplicit.eval_f, AllenCahn_2D_FD.py:207-228) */
+/* f = A u + inv_eps2 * u * (1 - u^nu_exp)   (allencahn_fullyimplicit.eval_f, AllenCahn_2D_FD.py:207-228);
+ * f_expl != NULL: f = A u and f_expl = inv_eps2 * u * (1 - u^nu_exp)  (allencahn_semiimplicit.eval_f, :278-303)      */
 int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
-                             const double* const* u, double* const* f, void* stream);
+                             const double* const* u, double* const* f, double* const* f_expl, void* stream);
 
 /* ---- K3: node solves ------------------------------------------------------------------------------------------------
  * Solve (I - factor_b * A) x_b = rhs_b for b < B with unpreconditioned CG following scipy.sparse.linalg.cg

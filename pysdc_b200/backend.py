@@ -40,7 +40,7 @@ def _declare(lib):
         "sdcb200_colloc_sweep": (c_int, [c_ll, c_int, c_int, c_int, c_int, PD, PD, PD, c_d, PP, _c_dp, PP, PP, _c_dp]),
         "sdcb200_colloc_residual": (c_int, [c_ll, c_int, c_int, c_int, PD, PP, _c_dp, PP, PP, PP, _c_dp, _c_dp]),
         "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
-        "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, _c_dp]),
+        "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "sdcb200_set_timeline": (c_int, [_c_dp]),
         "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, _c_dp, c_sz, _c_dp,
@@ -184,10 +184,12 @@ class CudaBackend:
         else:
             self._check(self.lib.sdcb200_heat_eval_f(lay.ndim, lay.n, bc, *tail))
 
-    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs):
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None):
+        """fexpls given: fs = A u, fexpls = reaction term (semi-implicit splitting); else fs = A u + reaction term."""
         self.launches += 1
         self._check(self.lib.sdcb200_allencahn_eval_f(lay.n, a_diag, a_off, inv_eps2, int(nu_exp), len(us),
-                                                      _ptr_array(us), _ptr_array(fs), self._stream()))
+                                                      _ptr_array(us), _ptr_array(fs),
+                                                      None if fexpls is None else _ptr_array(fexpls), self._stream()))
 
     # -- K3 / K4 ------------------------------------------------------------------------------------------------------
     def set_timeline(self, buf):

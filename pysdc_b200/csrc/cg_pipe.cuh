@@ -305,6 +305,7 @@ struct EvalPhase {
     double a_diag, a_off;
     double inv_eps2;      // Allen-Cahn reaction term  inv_eps2 * u * (1 - u^nu_exp) ; nu_exp == 0: none
     int nu_exp;
+    int split;            // 1: the reaction term goes to f_expl instead of being added to f (allencahn_semiimplicit)
     EvalField e[SDCB200_MAX_NODES];
 };
 
@@ -367,7 +368,7 @@ __device__ void pipe_pass(const Geom& g, const PUnits& U, const Sys* s, const Pi
                     hmap[0] = kMapPHalo;  // phase F: the field f is evaluated on (encoded in map slot P)
                 }
                 const bool halo_plane = NDIM == 3 && (c.zp < c.z0 || c.zp >= c.z1);
-                const bool profile = kProfile && pa.ev->e[b].f_expl != nullptr;
+                const bool profile = kProfile && pa.ev->e[b].f_expl != nullptr && !pa.ev->split;
                 int ncentre = halo_plane ? 0 : NCB + (kDiag ? 1 : 0) + (profile ? 1 : 0);
                 // which edges of the periodic domain does this tile touch?
                 const bool wT = PER && c.y0 == 0, wB = PER && c.y0 + kPY >= n;
@@ -575,11 +576,17 @@ __device__ void pipe_pass(const Geom& g, const PUnits& U, const Sys* s, const Pi
                                 px = __dmul_rn(px, ux);
                                 py = __dmul_rn(py, uy);
                             }
-                            f.x = __dadd_rn(mx, __dmul_rn(__dmul_rn(ex, ux), __dsub_rn(1.0, px)));
-                            f.y = __dadd_rn(my, __dmul_rn(__dmul_rn(ex, uy), __dsub_rn(1.0, py)));
+                            const double2 re = make_double2(__dmul_rn(__dmul_rn(ex, ux), __dsub_rn(1.0, px)),
+                                                            __dmul_rn(__dmul_rn(ex, uy), __dsub_rn(1.0, py)));
+                            if (pa.ev->split) {
+                                st2(out1 + id, re);  // f.expl (AllenCahn_2D_FD.py:300)
+                            } else {
+                                f.x = __dadd_rn(mx, re.x);
+                                f.y = __dadd_rn(my, re.y);
+                            }
                         }
                         st2(out0 + id, f);
-                        if (out1 != nullptr) {
+                        if (out1 != nullptr && !pa.ev->split) {
                             const double2 pr = lds2(&centre_box(s0, kDiagIdx)[ra + h][2 * lane]);
                             st2(out1 + id, make_double2(v0x ? __dmul_rn(pr.x, gt) : 0.0, v1x ? __dmul_rn(pr.y, gt) : 0.0));
                         }

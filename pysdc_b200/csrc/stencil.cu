@@ -14,6 +14,7 @@ struct EvalArgs {
     const double* profile;
     double a_diag, a_off, inv_eps2;
     int nu_exp;
+    int split;  // Allen-Cahn semi-implicit: reaction term into fexpl
 };
 
 __device__ __forceinline__ double ipow(double u, int k) {
@@ -106,9 +107,10 @@ int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
         a.ev.a_off = e.a_off;
         a.ev.inv_eps2 = e.inv_eps2;
         a.ev.nu_exp = e.nu_exp;
+        a.ev.split = e.split;
         for (int b = 0; b < nb; ++b) {
             a.ev.e[b].f = e.f[b0 + b];
-            a.ev.e[b].f_expl = e.profile != nullptr ? e.fexpl[b0 + b] : nullptr;
+            a.ev.e[b].f_expl = (e.profile != nullptr || e.split) ? e.fexpl[b0 + b] : nullptr;
             a.ev.e[b].gt = e.gt[b0 + b];
             if (int rc = encode_halo_maps(a.maps.m[b], kMapPHalo, e.g, e.u[b0 + b])) return rc;
             if (e.profile != nullptr)
@@ -198,7 +200,7 @@ int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off,
 }
 
 int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
-                             const double* const* u, double* const* f, void* stream) {
+                             const double* const* u, double* const* f, double* const* f_expl, void* stream) {
     SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES + 1, "B out of range");
     SDC_REQUIRE(n >= 2 && !(n & 1), "periodic grid needs an even number of points per dimension");
     SDC_REQUIRE(nu_exp >= 1, "nu must be a positive integer");
@@ -210,10 +212,15 @@ int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2
     a.a_off = a_off;
     a.inv_eps2 = inv_eps2;
     a.nu_exp = nu_exp;
+    a.split = f_expl != nullptr;
     for (int b = 0; b < B; ++b) {
         SDC_REQUIRE(ok16(u[b]) && ok16(f[b]), "u / f missing or misaligned");
         a.u[b] = u[b];
         a.f[b] = f[b];
+        if (f_expl != nullptr) {
+            SDC_REQUIRE(ok16(f_expl[b]), "f_expl missing or misaligned");
+            a.fexpl[b] = f_expl[b];
+        }
     }
     return launch_eval_pipe<2, true>(a, static_cast<cudaStream_t>(stream));
 }

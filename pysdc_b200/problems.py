@@ -455,11 +455,51 @@ class AllenCahnMixin(OutputMixin):
         return me
 
 
+class AllenCahnSemiMixin(AllenCahnMixin):
+    """``allencahn_semiimplicit`` (AllenCahn_2D_FD.py:261-376): the Laplacian implicit - a periodic CG solve of
+    (I - factor A) u = rhs with ``lin_tol`` / ``lin_maxiter`` on the TMA-pipelined solver -, the reaction term explicit."""
+
+    dtype_f = imex_mesh
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import imex_1st_order
+
+        return imex_1st_order
+
+    def eval_f_batch(self, us, ts, fs):
+        self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
+                                  [u.flat for u in us], [f.impl.flat for f in fs], [f.expl.flat for f in fs])
+        for _ in us:
+            self.work_counters["rhs"]()
+
+    def solve_system_batch(self, rhs, factors, xs, ts=None):
+        B = len(xs)
+        key = ("cg", B)
+        if key not in self._work:
+            self._work[key] = self._be.cg_workspace(self._lay, B)
+            self._cg_counters = self._be.zeros(8, dtype=torch.int32)
+        counters = self._cg_counters[:B]
+        counters.zero_()
+        log = getattr(self, "solve_log", None)
+        if log is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        self._be.heat_cg_solve(self._lay, BC_CODES["periodic"], [1.0 - f * self.a_diag for f in factors],
+                               [-(f * self.a_off) for f in factors], [r.flat for r in rhs], [x.flat for x in xs],
+                               self.lin_tol, self.lin_maxiter, self._work[key], counters)
+        if log is not None:
+            ev1.record()
+            log.append((ev0, ev1, counters.clone()))
+        self._counters[1:2] += counters.sum(dtype=torch.int32)  # work_counters['linear'] (AllenCahn_2D_FD.py:327-331)
+        self.lin_ncalls += B
+
+
 def _bind(base):
     """Concrete problem classes over a given ``Problem`` base class."""
     ns = {}
     for name, mixin in (("heatNd_unforced", HeatMixin), ("heatNd_forced", HeatForcedMixin),
-                        ("allencahn_fullyimplicit", AllenCahnMixin)):
+                        ("allencahn_fullyimplicit", AllenCahnMixin), ("allencahn_semiimplicit", AllenCahnSemiMixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
     return ns
 

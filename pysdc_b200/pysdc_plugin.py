@@ -20,5 +20,6 @@ from .transfer import mesh_to_mesh  # noqa: F401  (space_transfer_class for mult
 globals().update({k: v for k, v in _problems._bind(_PySDCProblem).items()})
 globals().update({k: v for k, v in _sweepers._bind(_PySDCSweeper).items()})
 
-__all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "generic_implicit",
+__all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "allencahn_semiimplicit",
+           "generic_implicit",
            "imex_1st_order", "mesh_to_mesh"]

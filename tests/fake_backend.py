@@ -259,11 +259,17 @@ class NumpyBackend:
             if profile is not None:
                 self._grid(lay, fexpls[i])[...] = self._grid(lay, profile) * gts[i]
 
-    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs):
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None):
         self.launches += 1
-        for u, f in zip(us, fs):
+        for i, (u, f) in enumerate(zip(us, fs)):
             x = self._grid(lay, u)
-            self._grid(lay, f)[...] = a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)
+            lap = a_diag * x + a_off * self._lap_sum(x, True)
+            react = inv_eps2 * x * (1.0 - x**nu_exp)
+            if fexpls is None:
+                self._grid(lay, f)[...] = lap + react
+            else:
+                self._grid(lay, f)[...] = lap
+                self._grid(lay, fexpls[i])[...] = react
 
     # ---- K5 ---------------------------------------------------------------------------------------------------------
     def upload_operator(self, W, col):

@@ -21,9 +21,9 @@ def test_operator_vectors(oracle, name):
     if "cg_iters" in g:
         assert P.counters["CG"].niter == int(g["cg_iters"])
     else:
-        assert P.counters["newton"].niter == int(g["newton"])
+        assert P.counters["newton"].niter == int(g["newton"]) if "newton" in g else P.counters["newton"].niter == 0
         assert P.counters["linear"].niter == int(g["linear"])
-    t_ex = 0.0 if spec["problem"] == "allencahn_fullyimplicit" else 0.1
+    t_ex = 0.0 if spec["problem"].startswith("allencahn") else 0.1
     assert _relerr(P.u_exact(t_ex), g["u_exact"]) == 0.0
 
 

@@ -48,7 +48,8 @@ def test_shipped_reference_is_unmodified():
 
 
 @pytest.mark.parametrize("name", ["run_heat3d_gi_minsrns_31", "run_heat3d_gi_lu_31", "run_heat2d_imex_lu_63",
-                                  "run_heat1d_imex_ie_step3A", "run_allencahn_gi_lu_64", "run_heat3d_gi_minsrflex_31"])
+                                  "run_heat1d_imex_ie_step3A", "run_allencahn_gi_lu_64", "run_heat3d_gi_minsrflex_31",
+                                  "run_allencahn_semi_imex_lu_64"])
 def test_reference_controller_drives_plugin_classes(plugin, name):
     from pySDC.core.sweeper import Sweeper
     from pySDC.helpers.stats_helper import get_sorted
