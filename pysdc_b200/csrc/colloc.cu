@@ -249,6 +249,21 @@ inline int stream_grid(long long count2) {
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+// Grid of a grid-stride streaming kernel: exactly ONE wave of co-resident CTAs (what the kernel's registers allow per SM
+// x SM count), so that no partially filled last wave trails behind (the collocation kernels hold 60-150 registers: 2-4
+// CTAs per SM, not the 8 that stream_grid assumes).
+template <auto kernel>
+int stream_grid_of(long long count2) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    }
+    const long long want = (count2 + kThreads - 1) / kThreads;
+    const long long cap = (long long)sm_count() * per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+#define LAUNCH(...) __VA_ARGS__<<<stream_grid_of<__VA_ARGS__>(a.count2), kThreads, 0, s>>>(a)
+
 }  // namespace
 
 void set_error(const std::string& msg) { g_last_error = msg; }
@@ -333,9 +348,8 @@ int sdcb200_colloc_apply(long long count, int nout, int nin, const double* W_hos
     a.count2 = count / 2;
     if (count == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = stream_grid(a.count2);
     switch (nout) {
-#define CASE(N) case N: colloc_apply_kernel<N><<<grid, kThreads, 0, s>>>(a); break;
+#define CASE(N) case N: LAUNCH(colloc_apply_kernel<N>); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
@@ -390,14 +404,13 @@ int sdcb200_colloc_sweep(long long count, int nout, int nj, int ncomp, int flags
     }
     if (count == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int grid = stream_grid(a.count2);
     const bool square = nj == nout && nout <= 4;  // (larger M: the register-resident variant would spill)
     switch (nout * 4 + (ncomp - 1) * 2 + (square ? 1 : 0)) {
 #define CASE(N) \
-    case 4 * N: colloc_sweep_kernel<N, 1, false><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 1: colloc_sweep_kernel<N, 1, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 2: colloc_sweep_kernel<N, 2, false><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 3: colloc_sweep_kernel<N, 2, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break;
+    case 4 * N: LAUNCH(colloc_sweep_kernel<N, 1, false>); break; \
+    case 4 * N + 1: LAUNCH(colloc_sweep_kernel<N, 1, (N <= 4)>); break; \
+    case 4 * N + 2: LAUNCH(colloc_sweep_kernel<N, 2, false>); break; \
+    case 4 * N + 3: LAUNCH(colloc_sweep_kernel<N, 2, (N <= 4)>); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
@@ -422,16 +435,12 @@ int sdcb200_colloc_residual(long long count, int M, int nj, int ncomp, const dou
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SDC_CUDA_OK(cudaMemsetAsync(resnorm_dev, 0, sizeof(double) * M, s));
     if (count == 0) return 0;
-    const int grid = stream_grid(a.count2);
     // (the register-resident variant pays off for the sweep kernel only: with the node values and the norms on top it
     // needs 120 registers and was measured at half the bandwidth of the generic loops)
-    const bool square = false;
-    switch (M * 4 + (ncomp - 1) * 2 + (square ? 1 : 0)) {
+    switch (M * 2 + (ncomp - 1)) {
 #define CASE(N) \
-    case 4 * N: colloc_residual_kernel<N, 1, false><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 1: colloc_residual_kernel<N, 1, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 2: colloc_residual_kernel<N, 2, false><<<grid, kThreads, 0, s>>>(a); break; \
-    case 4 * N + 3: colloc_residual_kernel<N, 2, (N <= 4)><<<grid, kThreads, 0, s>>>(a); break;
+    case 2 * N: LAUNCH(colloc_residual_kernel<N, 1, false>); break; \
+    case 2 * N + 1: LAUNCH(colloc_residual_kernel<N, 2, false>); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     }
