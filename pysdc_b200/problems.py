@@ -265,7 +265,8 @@ class HeatMixin(OutputMixin):
                 import weakref
 
                 self._work[B] = self._be.slab_cg_workspace(self._lay, self._comm, B)
-                weakref.finalize(self, self._work[B].close)  # unmap the peers' segments, free our own
+                if hasattr(self._work[B], "close"):
+                    weakref.finalize(self, self._work[B].close)  # unmap the peers' segments, free our own
             else:
                 self._work[B] = self._be.cg_workspace(self._lay, B)
         return self._work[B]
