@@ -70,21 +70,22 @@ enum PipePhase { kPhaseA = 0, kPhaseB = 1, kPhaseC = 2, kPhaseF = 3 };
 // grids) and up to three (four with a diagonal) tile-only boxes; it is sized for the largest phase of the variant.
 // EVAL: the variant of the eval_f kernel - one box with halo and one tile-only box per stage, so the pipeline can be
 // deeper (its single 10 KB box per step needs more steps in flight than the solver's 20-36 KB stages to keep HBM busy).
-template <bool PER, bool DIAG, bool EVAL = false>
+template <bool PER, bool DIAG, int EVAL = 0>
 struct PipeCfg {
     static constexpr int kWrap = PER ? kWrapSetBytes : 0;
     static constexpr int kBytesA = 2 * kHaloSlot + 2 * kWrap + (DIAG ? kCentreBoxBytes : 0);
     static constexpr int kBytesB = kHaloSlot + kWrap + (2 + (DIAG ? 1 : 0)) * kCentreBoxBytes;
-    static constexpr int kBytesF = kHaloSlot + kWrap + kCentreBoxBytes;
+    // eval_f: EVAL == 1 with a tile-only box (forcing profile), EVAL == 2 without - twice the pipeline depth
+    static constexpr int kBytesF = kHaloSlot + kWrap + (EVAL == 1 ? kCentreBoxBytes : 0);
     static constexpr int kStageBytes = EVAL ? kBytesF : (kBytesA > kBytesB ? kBytesA : kBytesB);
     // 2 CTAs per SM (16 consumer warps) must fit into 227 KB together with the static shared memory of the solver; the
     // kernels are held to 96 registers for that (5 warps of one SM sub-partition x 96 x 32 <= 16 K registers).
     // Measured alternative (-DSDCB200_ONE_CTA, profiles/r02/ab_one_vs_two_ctas.txt): ONE CTA per SM with 8 / 6 stages
     // is 8-10 % slower on every configuration - the consumers, not the bytes in flight, are what a second CTA adds.
 #ifdef SDCB200_ONE_CTA
-    static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 6 : 8);
+    static constexpr int kStages = EVAL == 2 ? (PER ? 8 : 10) : EVAL ? 5 : ((PER || DIAG) ? 6 : 8);
 #else
-    static constexpr int kStages = EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
+    static constexpr int kStages = EVAL == 2 ? (PER ? 8 : 10) : EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
 #endif
     // offsets inside a stage
     __host__ __device__ static constexpr int halo_off(int f) { return f * (kHaloSlot + kWrap); }
@@ -92,7 +93,7 @@ struct PipeCfg {
     __host__ __device__ static constexpr int centre_off(int nh, int f) { return nh * (kHaloSlot + kWrap) + f * kCentreBoxBytes; }
 };
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 10;
 struct PipeCtl {
     unsigned long long full[kMaxStages];
     unsigned long long empty[kMaxStages];
@@ -100,7 +101,7 @@ struct PipeCtl {
     int act_list[SDCB200_MAX_NODES];
     int nact;
 };
-template <bool PER, bool DIAG, bool EVAL = false>
+template <bool PER, bool DIAG, int EVAL = 0>
 struct PipeSmemT {
     using Cfg = PipeCfg<PER, DIAG, EVAL>;
     alignas(128) unsigned char st[Cfg::kStages][Cfg::kStageBytes];

@@ -74,9 +74,10 @@ struct EvalPipeArgs {
     PipeMaps maps;
 };
 
-template <int NDIM, bool PER>
-__global__ void __maxnreg__(112) eval_pipe_kernel(const __grid_constant__ EvalPipeArgs a) {
-    using Smem = PipeSmemT<PER, false, true>;
+// SLIM: no tile-only box in the stages (no forcing profile) -> 10 (periodic: 8) stages instead of 5
+template <int NDIM, bool PER, bool SLIM>
+__global__ void __maxnreg__(96) eval_pipe_kernel(const __grid_constant__ EvalPipeArgs a) {
+    using Smem = PipeSmemT<PER, false, SLIM ? 2 : 1>;
     extern __shared__ __align__(128) unsigned char pipe_smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(pipe_smem_raw);
     __shared__ CgShared sh;  // not used by this phase (no reductions)
@@ -93,12 +94,12 @@ __global__ void __maxnreg__(112) eval_pipe_kernel(const __grid_constant__ EvalPi
     pipe_pass<NDIM, PER, false, kPhaseF>(a.g, PU, nullptr, a.maps, sh, sm, nullptr, kstep, pa);
 }
 
-template <int NDIM, bool PER>
-int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
+template <int NDIM, bool PER, bool SLIM>
+int launch_eval_pipe_t(const EvalArgs& e, cudaStream_t s) {
     static thread_local EvalPipeArgs a;
-    const size_t smem = sizeof(PipeSmemT<PER, false, true>);
+    const size_t smem = sizeof(PipeSmemT<PER, false, SLIM ? 2 : 1>);
     int ctas = 0;
-    if (int rc = pipe_grid<eval_pipe_kernel<NDIM, PER>>(smem, &ctas)) return rc;
+    if (int rc = pipe_grid<eval_pipe_kernel<NDIM, PER, SLIM>>(smem, &ctas)) return rc;
     for (int b0 = 0; b0 < e.B; b0 += SDCB200_MAX_NODES) {  // at most MAX_NODES fields per launch (M + 1 fields in predict)
         const int nb = e.B - b0 < SDCB200_MAX_NODES ? e.B - b0 : SDCB200_MAX_NODES;
         a.g = e.g;
@@ -119,10 +120,15 @@ int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
         const PUnits PU = make_punits(e.g, nb, ctas);
         const long long units = (long long)nb * PU.per_field;
         const int grid = (int)(units < ctas ? units : ctas);
-        eval_pipe_kernel<NDIM, PER><<<grid, kPipeThreads, smem, s>>>(a);
+        eval_pipe_kernel<NDIM, PER, SLIM><<<grid, kPipeThreads, smem, s>>>(a);
         SDC_CUDA_OK(cudaGetLastError());
     }
     return 0;
+}
+
+template <int NDIM, bool PER>
+int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
+    return e.profile != nullptr ? launch_eval_pipe_t<NDIM, PER, false>(e, s) : launch_eval_pipe_t<NDIM, PER, true>(e, s);
 }
 
 template <int MODE>
