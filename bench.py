@@ -500,7 +500,7 @@ def run_b200(args):
         lvl.prob.solve_log = []
     tl_buf = None
     if args.timeline:
-        tl_buf = torch.zeros(12, dtype=torch.int64, device="cuda")
+        tl_buf = torch.zeros(16 + 4 * 1184, dtype=torch.int64, device="cuda")
         be.set_timeline(tl_buf)
         # host-side view of the same steps: CUDA-event time of the stages around the solver (halo exchange of the
         # initial guesses / of u before eval_f, collocation kernels, eval_f, the residual read)
@@ -549,6 +549,15 @@ def run_b200(args):
                         first_cta=dict(zip(keys, t8[:4])), last_cta=dict(zip(keys, t8[4:8])),
                         launch_shape=dict(ctas=int(raw[8]), units_per_system=int(raw[9]), planes_per_unit=int(raw[10])),
                         stages_ms=stages)
+        nct = int(raw[8])
+        if nct > 0:  # distribution over the CTAs of the grid: who is slow?
+            per = raw[16: 16 + 4 * nct].reshape(nct, 4) * 1e-6 / args.steps
+            work = per[:, 0]
+            order = np.argsort(work)
+            timeline["work_ms_over_ctas"] = dict(min=float(work.min()), median=float(np.median(work)), max=float(work.max()),
+                                                 slowest_ctas=[int(i) for i in order[-8:][::-1]],
+                                                 fastest_ctas=[int(i) for i in order[:8]],
+                                                 by_cta_every_16th=[round(float(v), 2) for v in work[::16]])
     clocks = sampler.stop() if rank == 0 else None
     fine_log = list(L.prob.solve_log)
     coarse_log = [e for lvl in levels[1:] for e in lvl.prob.solve_log]

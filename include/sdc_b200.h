@@ -131,7 +131,8 @@ size_t sdcb200_cg_workspace_bytes(int ndim, int n, int B);
  * launches add, in nanoseconds of %globaltimer, for the first CTA ([0..3]) and the last CTA ([4..7]) of the grid: [0] time
  * spent working between synchronisations (passes incl. pipeline fill / drain and tail), [1] waiting in the grid barrier,
  * [2] summing the partials, [3] in the cross-rank exchange of the sums (slab runs); [8..10] = grid size, units per system, planes per unit of
- * the last launch.  The buffer holds 12 values.  NULL switches it off.                                               */
+ * the last launch; [16 + 4*c + k]: the same four accumulators for every CTA c.  The buffer holds 16 + 4*1184 values.
+ * NULL switches it off.                                                                                             */
 int sdcb200_set_timeline(unsigned long long* dev_ns12);
 int sdcb200_heat_cg_solve(int ndim, int n, int bc, int B, const double* m_diag_host, const double* m_off_host,
                           const double* const* rhs, double* const* x, double rtol, int maxiter, int precond,

@@ -196,7 +196,7 @@ template <bool SLAB>
 __device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgShared& sh, const SlabLink* link,
                                            unsigned long long& seq, const int* slots, const int* systems, int nv,
                                            unsigned long long* tl = nullptr) {
-    const bool rec = tl != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+    const bool rec = tl != nullptr && threadIdx.x == 0;
     unsigned long long t0 = 0, t1 = 0, t2 = 0;
     if (rec) t0 = global_ns();
     if (SLAB) grid_barrier_sys(bar);
@@ -211,11 +211,18 @@ __device__ __forceinline__ void reduce_all(double* partials, unsigned* bar, CgSh
     else __syncthreads();
     if (rec) {
         const unsigned long long t3 = global_ns();
-        unsigned long long* a = tl + (blockIdx.x == 0 ? 0 : 4);
-        a[0] += t0 - sh.t_last;
-        a[1] += t1 - t0;
-        a[2] += t2 - t1;
-        a[3] += t3 - t2;
+        unsigned long long* per_cta = tl + 16 + 4 * blockIdx.x;  // every CTA: its own four accumulators
+        per_cta[0] += t0 - sh.t_last;
+        per_cta[1] += t1 - t0;
+        per_cta[2] += t2 - t1;
+        per_cta[3] += t3 - t2;
+        if (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) {
+            unsigned long long* a = tl + (blockIdx.x == 0 ? 0 : 4);
+            a[0] += t0 - sh.t_last;
+            a[1] += t1 - t0;
+            a[2] += t2 - t1;
+            a[3] += t3 - t2;
+        }
         sh.t_last = t3;
     }
 }
