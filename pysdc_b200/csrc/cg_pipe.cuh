@@ -40,10 +40,14 @@
 namespace sdcb200 {
 
 constexpr int kPX = 64;             // tile width in doubles
-constexpr int kPY = 16;             // tile rows
+#ifdef SDCB200_SHORT_TILES          // A/B switch: round-1 shape, 64x16 tiles, 8 consumer warps, 2 CTAs per SM
+constexpr int kPY = 16;
+#else
+constexpr int kPY = 32;             // tile rows: ONE CTA per SM with 16 consumer warps (see PipeCfg)
+#endif
 constexpr int kPHX = kPX + 4;       // staged row with halo: cols 0,1 = x0-2, x0-1 | 2..65 tile | 66,67 = x0+64, x0+65
-constexpr int kPHY = kPY + 2;       // staged rows with halo: row 0 = y0-1, rows 1..16 tile, row 17 = y0+16
-constexpr int kPipeConsumers = 8;   // consumer warps
+constexpr int kPHY = kPY + 2;       // staged rows with halo: row 0 = y0-1, rows 1..kPY tile, row kPY+1 = y0+kPY
+constexpr int kPipeConsumers = kPY / 2;   // consumer warps: two adjacent rows each
 constexpr int kPipeThreads = 32 * (kPipeConsumers + 1);
 
 constexpr int kHaloBoxBytes = kPHY * kPHX * 8;   // 9792
@@ -51,7 +55,7 @@ constexpr int kCentreBoxBytes = kPY * kPX * 8;   // 8192
 constexpr int kHaloSlot = (kHaloBoxBytes + 127) / 128 * 128;  // every box starts 128-byte aligned in smem
 constexpr int kWrapRowBytes = kPHX * 8;          // 544: one row with halo columns
 constexpr int kWrapColBytes = kPHY * 2 * 8;      // 288: a column pair over the rows with halo
-constexpr int kWrapRowSlot = 640, kWrapColSlot = 384;
+constexpr int kWrapRowSlot = 640, kWrapColSlot = (kWrapColBytes + 127) / 128 * 128;
 constexpr int kWrapSetBytes = 2 * kWrapRowSlot + 2 * kWrapColSlot;  // 2048
 
 // what lies across the periodic edge of a tile: row y0-1 -> n-1 (T), row y0+16 -> 0 (B), columns x0-2,x0-1 -> n-2,n-1 (L),
