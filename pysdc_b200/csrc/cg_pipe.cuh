@@ -40,10 +40,10 @@
 namespace sdcb200 {
 
 constexpr int kPX = 64;             // tile width in doubles
-#ifdef SDCB200_SHORT_TILES          // A/B switch: round-1 shape, 64x16 tiles, 8 consumer warps, 2 CTAs per SM
-constexpr int kPY = 16;
+#ifdef SDCB200_TALL_TILES           // A/B switch: 64x32 tiles, ONE CTA per SM with 16 consumer warps - measured equal
+constexpr int kPY = 32;             // to the default within 1 % on configs 2, 3, 4 (profiles/r02/ab_tall_vs_short_tiles.txt)
 #else
-constexpr int kPY = 32;             // tile rows: ONE CTA per SM with 16 consumer warps (see PipeCfg)
+constexpr int kPY = 16;             // tile rows
 #endif
 constexpr int kPHX = kPX + 4;       // staged row with halo: cols 0,1 = x0-2, x0-1 | 2..65 tile | 66,67 = x0+64, x0+65
 constexpr int kPHY = kPY + 2;       // staged rows with halo: row 0 = y0-1, rows 1..kPY tile, row kPY+1 = y0+kPY
