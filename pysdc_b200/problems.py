@@ -446,11 +446,32 @@ class AllenCahnMixin(OutputMixin):
         self.solve_system_batch([rhs], [factor], [me], [t])
         return me
 
+    def _rhs_total(self, f):
+        """Full right-hand side as one field (the semi-implicit class adds its two components)."""
+        return f
+
     def u_exact(self, t, u_init=None, t_init=None):
-        """AllenCahn_2D_FD.py:230-257; only the initial condition (t = 0) is available without a reference integrator."""
+        """AllenCahn_2D_FD.py:230-257: the tanh circle at t = 0; for t > 0 a reference solution from scipy's
+        ``solve_ivp`` with tolerances of 100 ulp (core/problem.py:118-152), its right-hand side evaluated by the device
+        ``eval_f`` (each call uploads the state and downloads f: a checking aid, as in the reference, not a fast path)."""
         me = self.dtype_u(self.init, val=0.0)
         if t > 0:
-            raise NotImplementedError("u_exact(t > 0) needs the reference's scipy reference solution; not on the device")
+            from scipy.integrate import solve_ivp
+
+            rhs_counter = self.work_counters["rhs"]
+
+            def eval_rhs(tt, u):
+                v = self.dtype_u(self.init)
+                v[:] = u.reshape(self.nvars)
+                out = self._rhs_total(self.eval_f(v, tt)).get().flatten()
+                rhs_counter.decrement()  # reference evaluations are not part of the run's work
+                return out
+
+            u0 = self.u_exact(0.0).get() if u_init is None else np.asarray(u_init.get() if hasattr(u_init, "get") else u_init) * 1.0
+            tol = 100 * np.finfo(float).eps
+            sol = solve_ivp(eval_rhs, (0 if t_init is None else t_init, t), u0.flatten(), atol=tol, rtol=tol)
+            me[:] = sol.y[:, -1].reshape(self.nvars)
+            return me
         X, Y = np.meshgrid(self.xvalues, self.xvalues)
         me[:] = np.tanh((self.radius - np.sqrt(X**2 + Y**2)) / (np.sqrt(2) * self.eps))
         return me
@@ -467,6 +488,9 @@ class AllenCahnSemiMixin(AllenCahnMixin):
         from .sweepers import imex_1st_order
 
         return imex_1st_order
+
+    def _rhs_total(self, f):
+        return f.impl + f.expl  # AllenCahn_2D_FD.py:364-366
 
     def eval_f_batch(self, us, ts, fs):
         self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),

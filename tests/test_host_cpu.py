@@ -175,3 +175,28 @@ def test_output_file_of_device_fields(tmp_path):
 
 def test_spatial_accuracy_of_the_higher_order_stencils():
     pc.check_spatial_accuracy(pmax=7)
+
+
+def test_allencahn_reference_solution_for_t_gt_0():
+    """u_exact(t > 0) of the Allen-Cahn classes (AllenCahn_2D_FD.py:230-257, :347-376): scipy's solve_ivp on the device
+    eval_f; an SDC run to the same time must agree with it to the accuracy of the run, the work counters must not count
+    the reference evaluations."""
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.problems import allencahn_fullyimplicit, allencahn_semiimplicit
+    from pysdc_b200.sweepers import generic_implicit, imex_1st_order
+
+    pp = dict(nvars=(16, 16), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-10, lin_tol=1e-11, lin_maxiter=200, radius=0.25)
+    for cls, sw in ((allencahn_fullyimplicit, generic_implicit), (allencahn_semiimplicit, imex_1st_order)):
+        c = controller_nonMPI(1, dict(logger_level=40), dict(
+            problem_class=cls, problem_params=pp, sweeper_class=sw,
+            sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"), level_params=dict(dt=5e-4, restol=1e-10),
+            step_params=dict(maxiter=50)))
+        P = c.MS[0].levels[0].prob
+        uend, _ = c.run(u0=P.u_exact(0.0), t0=0.0, Tend=2e-3)
+        n_rhs = P.work_counters["rhs"].niter
+        uex = P.u_exact(2e-3)
+        assert P.work_counters["rhs"].niter == n_rhs
+        assert type(uex) is P.dtype_u and abs(uex - uend) < 1e-6 * abs(uex), (cls.__name__, abs(uex - uend))  # (time-discretisation error)
+        # continuing a reference solution from an intermediate state (u_init, t_init)
+        umid = P.u_exact(1e-3)
+        assert abs(P.u_exact(2e-3, u_init=umid, t_init=1e-3) - uex) < 1e-10
