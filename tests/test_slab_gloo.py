@@ -118,6 +118,12 @@ def _worker(rank, world, port, n, out_dir):
         np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.gather())
         np.save(os.path.join(out_dir, f"niter_{rank}.npy"), np.array(niter))
         np.save(os.path.join(out_dir, f"cg_{rank}.npy"), np.array(P.work_counters["CG"].niter))
+        # output of slab fields (fields_io.py): every rank writes its planes into the global record of a FieldsIO file
+        path = os.path.join(out_dir, "slab.pySDC")
+        out = P.getOutputFile(path)
+        out.addField(0.0, P.processSolutionForOutput(P.u_exact(0.0)))
+        out.addField(1e-3, P.processSolutionForOutput(uend))
+        out.flush()
         uend, niter, P = _run_imex(n, comm)
         assert abs(P.u_exact(1e-2) - uend) < 0.05  # global max-norm through the communicator
         np.save(os.path.join(out_dir, f"imex_uend_{rank}.npy"), uend.gather())
@@ -150,6 +156,13 @@ def test_slab_step_matches_serial(tmp_path, world, n):
             assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
             assert list(np.load(os.path.join(tmp_path, f"niter_{r}.npy"))) == niter
             assert abs(int(np.load(os.path.join(tmp_path, f"cg_{r}.npy"))) - P.work_counters["CG"].niter) <= 2
+        # the file the ranks wrote together holds the GLOBAL fields (readable without any communicator)
+        from pysdc_b200.fields_io import RectilinearFile
+
+        f = RectilinearFile.fromFile(os.path.join(tmp_path, "slab.pySDC"))
+        assert f.times == [0.0, 1e-3] and f.gridSizes == [n, n, n]
+        assert np.array_equal(f.readField(0)[1][0], P.u_exact(0.0).get())
+        assert np.max(np.abs(f.readField(1)[1][0] - ref)) / np.max(np.abs(ref)) < 1e-12
         uend, niter, _ = _run_imex(n, None)
         ref = uend.get()
         for r in range(world):
