@@ -130,6 +130,9 @@ template <int NDIM, bool PER>
 int launch_eval_pipe(const EvalArgs& e, cudaStream_t s) {
     // The SLIM variant (no tile-only slot, 10 stages instead of 5) was measured SLOWER at 511^3 (0.74 vs 0.83-0.86 of the
     // measured HBM peak, profiles/r02/bench_driverlike_r2l.json vs bench_c3_r2k.json): the 5-stage shape is used always.
+#ifdef SDCB200_EVAL_SLIM
+    if (e.profile == nullptr) return launch_eval_pipe_t<NDIM, PER, true>(e, s);
+#endif
     return launch_eval_pipe_t<NDIM, PER, false>(e, s);
 }
 
