@@ -86,13 +86,16 @@ struct PipeCfg {
     // kernels are held to 96 registers for that (5 warps of one SM sub-partition x 96 x 32 <= 16 K registers).
     // Measured alternative (-DSDCB200_ONE_CTA, profiles/r02/ab_one_vs_two_ctas.txt): ONE CTA per SM with 8 / 6 stages
     // is 8-10 % slower on every configuration - the consumers, not the bytes in flight, are what a second CTA adds.
+#ifndef SDCB200_EVAL_STAGES
+#define SDCB200_EVAL_STAGES 5
+#endif
 #ifndef SDCB200_SLIM_STAGES
 #define SDCB200_SLIM_STAGES 7  // eval_f without the tile-only slot (experiment: scripts/gpu_r2p.sh)
 #endif
 #ifdef SDCB200_ONE_CTA
     static constexpr int kStages = EVAL == 2 ? (PER ? 8 : 10) : EVAL ? 5 : ((PER || DIAG) ? 6 : 8);
 #else
-    static constexpr int kStages = EVAL == 2 ? SDCB200_SLIM_STAGES : EVAL ? 5 : ((PER || DIAG) ? 3 : 4);
+    static constexpr int kStages = EVAL == 2 ? SDCB200_SLIM_STAGES : EVAL ? SDCB200_EVAL_STAGES : ((PER || DIAG) ? 3 : 4);
 #endif
     // offsets inside a stage
     __host__ __device__ static constexpr int halo_off(int f) { return f * (kHaloSlot + kWrap); }
