@@ -65,7 +65,30 @@ def config4(n, steps=2):
     run_large(f"run_config4_allencahn_gi_lu_{n}", spec, subsample=max(1, n // 64))
 
 
-FAMILIES = {"config2_511": lambda: config2(511), "config2_1023": lambda: config2(1023),
+def config3(n, K=4):
+    """Config 3 scaled down with the bench settings (restol=-1, K sweeps, seeded random field)."""
+    spec = dict(problem="heatNd_unforced", sweeper="generic_implicit",
+                problem_params=dict(nvars=[n, n, n], nu=0.1, freq=[1, 1, 1], bc="dirichlet-zero", solver_type="CG",
+                                    lintol=1e-12, liniter=10000),
+                sweeper_params=dict(num_nodes=4, quad_type="RADAU-RIGHT", QI="MIN-SR-NS", initial_guess="spread"),
+                level_params=dict(dt=1e-3, restol=-1), step_params=dict(maxiter=K),
+                t0=0.0, Tend=1e-3, u0="random", seed=1234)
+    d = mg.make_description(spec)
+    c = mg.controller_nonMPI(num_procs=1, controller_params={"logger_level": 40, "hook_class": [mg.LogWork]}, description=d)
+    P = c.MS[0].levels[0].prob
+    u0 = mg.initial_value(P, spec)
+    uend, stats = c.run(u0=u0, t0=0.0, Tend=1e-3)
+    gs = mg.get_sorted
+    niter = [int(v) for _, v in gs(stats, type="niter", sortby="time")]
+    res = np.array([[float(v) for _, v in gs(stats, type="residual_post_iteration", sortby="iter")]])
+    sub = max(1, (n + 1) // 32)
+    mg.save(f"run_config3_heat3d_gi_minsrns_{n}_K{K}", dict(spec, subsample=sub), niter=np.array(niter), times=np.array([0.0]),
+            residuals=res, uend_maxabs=np.array(float(abs(uend))), uend_sub=np.asarray(uend)[::sub, ::sub, ::sub].copy(),
+            work_CG=np.array([int(v) for _, v in gs(stats, type="work_CG", sortby="time")]))
+    print(f"  config3 {n}: niter {niter}, |uend| {float(abs(uend))!r}", flush=True)
+
+
+FAMILIES = {"config3_127": lambda: config3(127), "config2_511": lambda: config2(511), "config2_1023": lambda: config2(1023),
             "config2_2047": lambda: config2(2047), "config4_256": lambda: config4(256),
             "config4_512": lambda: config4(512), "config4_1024": lambda: config4(1024)}
 
