@@ -110,9 +110,11 @@ int sdcb200_heat_eval_f(int ndim, int n, int bc, double a_diag, double a_off, in
                         const double* const* u, double* const* f_impl,
                         const double* profile, const double* gt_host, double* const* f_expl, void* stream);
 
-/* f = A u + inv_eps2 * u * (1 - u^nu_exp)   (allencahn_fullyimplicit.eval_f, AllenCahn_2D_FD.py:207-228);
- * f_expl != NULL: f = A u and f_expl = inv_eps2 * u * (1 - u^nu_exp)  (allencahn_semiimplicit.eval_f, :278-303)      */
-int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
+/* split == 0: f = A u + inv_eps2 * u * (1 - u^nu_exp)   (allencahn_fullyimplicit.eval_f, AllenCahn_2D_FD.py:207-228);
+ * split == 1: f = A u, f_expl = inv_eps2 * u * (1 - u^nu_exp)             (allencahn_semiimplicit.eval_f, :278-303);
+ * split == 2: f = A u - inv_eps2 * u^(nu_exp+1), f_expl = inv_eps2 * u    (allencahn_semiimplicit_v2.eval_f, :402-424).
+ * f_expl is NULL exactly when split == 0.                                                                            */
+int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int split, int B,
                              const double* const* u, double* const* f, double* const* f_expl, void* stream);
 
 /* ---- K3: node solves ------------------------------------------------------------------------------------------------
@@ -201,12 +203,13 @@ int sdcb200_heat_cg_solve_ho(int ndim, int n, int bc, int order, const double* c
  * rhs_b, whole solve in one persistent launch (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205; B > 1:
  * the independent node systems of a diagonal QDelta).  u[b]: in = initial guess, out = solution.  Systems leave the
  * Newton loop and the inner CG individually.  counters_dev[0] += Newton iterations, counters_dev[1] += CG iterations
- * (summed over the systems).  inexact_ratio <= 0 disables :176-177.  The inner CG runs the TMA-pipelined passes with
+ * (summed over the systems).  inexact_ratio <= 0 disables :176-177.  variant == 1: the Newton system of
+ * allencahn_semiimplicit_v2 (:426-466), u - factor (A u - u^(nu+1)/eps^2) = rhs.  The inner CG runs the TMA-pipelined passes with
  * periodic wrap boxes and the Jacobian diagonal as a tile-only box.  work: sdcb200_newton_workspace_bytes(n, B) bytes,
  * 256-byte aligned, zero-filled before its first use.                                                               */
 size_t sdcb200_newton_workspace_bytes(int n, int B);
-int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, double a_diag, double a_off, double inv_eps2,
-                                   int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
+int sdcb200_allencahn_newton_solve(int n, int B, int variant, const double* factor_host, double a_diag, double a_off,
+                                   double inv_eps2, int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
                                    int newton_maxiter, double lin_tol, int lin_maxiter, double inexact_ratio,
                                    void* work, size_t work_bytes, int* counters_dev, void* stream);
 

@@ -40,7 +40,7 @@ def _declare(lib):
         "sdcb200_colloc_sweep": (c_int, [c_ll, c_int, c_int, c_int, c_int, PD, PD, PD, c_d, PP, _c_dp, PP, PP, _c_dp]),
         "sdcb200_colloc_residual": (c_int, [c_ll, c_int, c_int, c_int, PD, PP, _c_dp, PP, PP, PP, _c_dp, _c_dp]),
         "sdcb200_heat_eval_f": (c_int, [c_int, c_int, c_int, c_d, c_d, c_int, PP, PP, _c_dp, PD, PP, _c_dp]),
-        "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, PP, PP, PP, _c_dp]),
+        "sdcb200_allencahn_eval_f": (c_int, [c_int, c_d, c_d, c_d, c_int, c_int, c_int, PP, PP, PP, _c_dp]),
         "sdcb200_cg_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "sdcb200_set_timeline": (c_int, [_c_dp]),
         "sdcb200_heat_cg_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PP, PP, c_d, c_int, c_int, _c_dp, c_sz, _c_dp,
@@ -60,7 +60,7 @@ def _declare(lib):
         "sdcb200_heat_cg_solve_ho": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_int, PD, PP, PP, c_d, c_int, _c_dp,
                                              c_sz, _c_dp, _c_dp]),
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int, c_int]),
-        "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
+        "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
                                                    c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
     }
     for name, (res, args) in sig.items():
@@ -184,10 +184,12 @@ class CudaBackend:
         else:
             self._check(self.lib.sdcb200_heat_eval_f(lay.ndim, lay.n, bc, *tail))
 
-    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None):
-        """fexpls given: fs = A u, fexpls = reaction term (semi-implicit splitting); else fs = A u + reaction term."""
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None, split=None):
+        """fexpls given: fs = A u, fexpls = reaction term (semi-implicit splitting, split = 1) or fs = A u - u^(nu+1)/eps^2,
+        fexpls = u/eps^2 (split = 2); else fs = A u + reaction term."""
         self.launches += 1
-        self._check(self.lib.sdcb200_allencahn_eval_f(lay.n, a_diag, a_off, inv_eps2, int(nu_exp), len(us),
+        split = (0 if fexpls is None else 1) if split is None else int(split)
+        self._check(self.lib.sdcb200_allencahn_eval_f(lay.n, a_diag, a_off, inv_eps2, int(nu_exp), split, len(us),
                                                       _ptr_array(us), _ptr_array(fs),
                                                       None if fexpls is None else _ptr_array(fexpls), self._stream()))
 
@@ -286,11 +288,12 @@ class CudaBackend:
         return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
 
     def allencahn_newton_solve(self, lay, factors, a_diag, a_off, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter,
-                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
-        """Newton + inner CG for the len(us) systems (rhs[b], factors[b]) in ONE persistent launch, in place on us[b]."""
+                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev, variant=0):
+        """Newton + inner CG for the len(us) systems (rhs[b], factors[b]) in ONE persistent launch, in place on us[b].
+        variant 1: the implicit part of allencahn_semiimplicit_v2."""
         self.launches += 1
         self._check(self.lib.sdcb200_allencahn_newton_solve(
-            lay.n, len(us), _dbl_array(factors), a_diag, a_off, inv_eps2, int(nu_exp), _ptr_array(rhs), _ptr_array(us),
+            lay.n, len(us), int(variant), _dbl_array(factors), a_diag, a_off, inv_eps2, int(nu_exp), _ptr_array(rhs), _ptr_array(us),
             float(newton_tol), int(newton_maxiter), float(lin_tol), int(lin_maxiter),
             float(inexact_ratio or 0.0), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(), self._stream()))
 

@@ -527,22 +527,27 @@ __global__ void __maxnreg__(SDCB200_SOLVER_MAXNREG) newton_pipe_kernel(const __g
                     stencil_unit<2, true>(g, U, N.u, unit, [&](long long idx, double2 c, double2 nb, bool, bool) {
                         const double2 rhs = ld2(N.rhs + idx);
                         double2 gv, dv;
-                        {
-                            const double Au = fma(a.a_off, nb.x, a.a_diag * c.x);
-                            const double un = ipow(c.x, a.nu_exp);
-                            const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.x), __dsub_rn(1.0, un));
-                            gv.x = __dsub_rn(__dsub_rn(c.x, __dmul_rn(factor, __dadd_rn(Au, react))), rhs.x);
-                            const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
-                            dv.x = __dsub_rn(1.0, __dmul_rn(factor, __dadd_rn(a.a_diag, jr)));
+                        const double cs[2] = {c.x, c.y}, nbs[2] = {nb.x, nb.y}, rh[2] = {rhs.x, rhs.y};
+                        double gs[2], ds[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double u = cs[e];
+                            const double Au = fma(a.a_off, nbs[e], a.a_diag * u);
+                            const double un = ipow(u, a.nu_exp);
+                            if (a.variant == 0) {  // AllenCahn_2D_FD.py:170,183
+                                const double react = __dmul_rn(__dmul_rn(a.inv_eps2, u), __dsub_rn(1.0, un));
+                                gs[e] = __dsub_rn(__dsub_rn(u, __dmul_rn(factor, __dadd_rn(Au, react))), rh[e]);
+                                const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
+                                ds[e] = __dsub_rn(1.0, __dmul_rn(factor, __dadd_rn(a.a_diag, jr)));
+                            } else {  // allencahn_semiimplicit_v2, :447,453: implicit part A u - u^(nu+1)/eps^2
+                                const double term = __dmul_rn(a.inv_eps2, __dmul_rn(un, u));
+                                gs[e] = __dsub_rn(__dsub_rn(u, __dmul_rn(factor, __dsub_rn(Au, term))), rh[e]);
+                                const double jr = __dmul_rn(a.inv_eps2, __dmul_rn((double)(a.nu_exp + 1), un));
+                                ds[e] = __dsub_rn(1.0, __dmul_rn(factor, __dsub_rn(a.a_diag, jr)));
+                            }
                         }
-                        {
-                            const double Au = fma(a.a_off, nb.y, a.a_diag * c.y);
-                            const double un = ipow(c.y, a.nu_exp);
-                            const double react = __dmul_rn(__dmul_rn(a.inv_eps2, c.y), __dsub_rn(1.0, un));
-                            gv.y = __dsub_rn(__dsub_rn(c.y, __dmul_rn(factor, __dadd_rn(Au, react))), rhs.y);
-                            const double jr = __dmul_rn(a.inv_eps2, __dsub_rn(1.0, __dmul_rn((double)(a.nu_exp + 1), un)));
-                            dv.y = __dsub_rn(1.0, __dmul_rn(factor, __dadd_rn(a.a_diag, jr)));
-                        }
+                        gv = make_double2(gs[0], gs[1]);
+                        dv = make_double2(ds[0], ds[1]);
                         st2(gvec + idx, gv);
                         st2(dvec + idx, dv);
                         st2(S.x + idx, make_double2(0.0, 0.0));
@@ -870,13 +875,14 @@ int sdcb200_heat_cg_solve_slab(int n, int nz, int nz_max, int bc, int B, const d
 
 size_t sdcb200_newton_workspace_bytes(int n, int B) { return work_layout(2, n, 6 * B).total; }
 
-int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, double a_diag, double a_off, double inv_eps2,
-                                   int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
+int sdcb200_allencahn_newton_solve(int n, int B, int variant, const double* factor_host, double a_diag, double a_off,
+                                   double inv_eps2, int nu_exp, const double* const* rhs, double* const* u, double newton_tol,
                                    int newton_maxiter, double lin_tol, int lin_maxiter, double inexact_ratio, void* work,
                                    size_t work_bytes, int* counters_dev, void* stream) {
     SDC_REQUIRE(n >= 2 && !(n & 1), "periodic grid needs an even number of points per dimension");
     SDC_REQUIRE(nu_exp >= 1, "nu must be a positive integer");
     SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES, "B out of range");
+    SDC_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (fully implicit) or 1 (semi-implicit v2)");
     const WorkLayout w = work_layout(2, n, 6 * B);
     SDC_REQUIRE(work != nullptr && work_bytes >= w.total, "workspace too small (see sdcb200_newton_workspace_bytes)");
     SDC_REQUIRE((reinterpret_cast<size_t>(work) & 255u) == 0, "workspace must be 256-byte aligned");
@@ -891,6 +897,7 @@ int sdcb200_allencahn_newton_solve(int n, int B, const double* factor_host, doub
     a.a_off = a_off;
     a.inv_eps2 = inv_eps2;
     a.nu_exp = nu_exp;
+    a.variant = variant;
     char* base = static_cast<char*>(work);
     for (int b = 0; b < B; ++b) {
         SDC_REQUIRE(rhs[b] && u[b] && !(reinterpret_cast<size_t>(rhs[b]) & 15u) && !(reinterpret_cast<size_t>(u[b]) & 15u),

@@ -42,6 +42,7 @@ struct NewtonArgs {
     NewtonSys ns[SDCB200_MAX_NODES];
     double a_diag, a_off, inv_eps2;
     int nu_exp;
+    int variant;   // 0: allencahn_fullyimplicit; 1: allencahn_semiimplicit_v2 (implicit part A u - u^(nu+1)/eps^2)
     double newton_tol, lin_tol, inexact_ratio;
     int newton_maxiter, lin_maxiter;
     int* counters_out;  // [0] += newton iterations, [1] += CG iterations (summed over the systems)

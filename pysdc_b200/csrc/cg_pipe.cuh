@@ -316,7 +316,8 @@ struct EvalPhase {
     double a_diag, a_off;
     double inv_eps2;      // Allen-Cahn reaction term  inv_eps2 * u * (1 - u^nu_exp) ; nu_exp == 0: none
     int nu_exp;
-    int split;            // 1: the reaction term goes to f_expl instead of being added to f (allencahn_semiimplicit)
+    int split;            // 1: the reaction term goes to f_expl instead of being added to f (allencahn_semiimplicit);
+                          // 2: f = A u - inv_eps2 * u^(nu+1), f_expl = inv_eps2 * u (allencahn_semiimplicit_v2)
     EvalField e[SDCB200_MAX_NODES];
 };
 
@@ -589,7 +590,11 @@ __device__ void pipe_pass(const Geom& g, const PUnits& U, const Sys* s, const Pi
                             }
                             const double2 re = make_double2(__dmul_rn(__dmul_rn(ex, ux), __dsub_rn(1.0, px)),
                                                             __dmul_rn(__dmul_rn(ex, uy), __dsub_rn(1.0, py)));
-                            if (pa.ev->split) {
+                            if (pa.ev->split == 2) {  // AllenCahn_2D_FD.py:421-422
+                                f.x = __dsub_rn(mx, __dmul_rn(ex, __dmul_rn(px, ux)));
+                                f.y = __dsub_rn(my, __dmul_rn(ex, __dmul_rn(py, uy)));
+                                st2(out1 + id, make_double2(__dmul_rn(ex, ux), __dmul_rn(ex, uy)));
+                            } else if (pa.ev->split) {
                                 st2(out1 + id, re);  // f.expl (AllenCahn_2D_FD.py:300)
                             } else {
                                 f.x = __dadd_rn(mx, re.x);

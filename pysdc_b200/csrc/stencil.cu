@@ -210,7 +210,7 @@ int sdcb200_heat_eval_f_slab(int n, int nz, int bc, double a_diag, double a_off,
     return profile ? dispatch_eval<1>(a, s) : dispatch_eval<0>(a, s);
 }
 
-int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int B,
+int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2, int nu_exp, int split, int B,
                              const double* const* u, double* const* f, double* const* f_expl, void* stream) {
     SDC_REQUIRE(B >= 1 && B <= SDCB200_MAX_NODES + 1, "B out of range");
     SDC_REQUIRE(n >= 2 && !(n & 1), "periodic grid needs an even number of points per dimension");
@@ -223,7 +223,8 @@ int sdcb200_allencahn_eval_f(int n, double a_diag, double a_off, double inv_eps2
     a.a_off = a_off;
     a.inv_eps2 = inv_eps2;
     a.nu_exp = nu_exp;
-    a.split = f_expl != nullptr;
+    SDC_REQUIRE(split >= 0 && split <= 2 && (split == 0) == (f_expl == nullptr), "split / f_expl mismatch");
+    a.split = split;
     for (int b = 0; b < B; ++b) {
         SDC_REQUIRE(ok16(u[b]) && ok16(f[b]), "u / f missing or misaligned");
         a.u[b] = u[b];

@@ -387,10 +387,9 @@ class AllenCahnMixin(OutputMixin):
         self.a_diag = (-2.0 * 2) / self.dx**2
         self._be = get_backend()
         self._lay = get_layout(nvars)
-        self._counters = self._be.zeros(6, dtype=torch.int32)  # [newton, linear, rhs(unused), -, per-launch newton, linear]
+        # [work newton, work linear, rhs(unused), -, per-launch newton, per-launch linear, newton_itercount, lin_itercount]
+        self._counters = self._be.zeros(8, dtype=torch.int32)
         self._work = {}
-        self.newton_itercount = 0  # kept for API compatibility; the live counts are in work_counters
-        self.lin_itercount = 0
         self.newton_ncalls = 0
         self.lin_ncalls = 0
         self.work_counters["newton"] = DeviceWorkCounter(self._counters[0:1])
@@ -400,6 +399,16 @@ class AllenCahnMixin(OutputMixin):
     @property
     def ndim(self):
         return 2
+
+    # the reference's plain-int totals (AllenCahn_2D_FD.py:127-130,202-203,347-348); the counts live on the device, so
+    # reading one synchronises
+    @property
+    def newton_itercount(self):
+        return int(self._counters[6].item())
+
+    @property
+    def lin_itercount(self):
+        return int(self._counters[7].item())
 
     @classmethod
     def get_default_sweeper_class(cls):
@@ -431,15 +440,22 @@ class AllenCahnMixin(OutputMixin):
         if log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        self._be.allencahn_newton_solve(self._lay, list(factors), self.a_diag, self.a_off, 1.0 / self.eps**2,
-                                        int(self.nu), [r.flat for r in rhs], [x.flat for x in xs], self.newton_tol,
-                                        self.newton_maxiter, self.lin_tol, self.lin_maxiter, self.inexact_linear_ratio,
-                                        self._work[B], counters)
+        self._newton_launch(list(factors), rhs, xs, self._work[B], counters)
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, counters.clone()))
-        self._counters[0:2] += counters
+        self._count_newton(counters)
         self.newton_ncalls += B
+
+    def _newton_launch(self, factors, rhs, xs, work, counters):
+        self._be.allencahn_newton_solve(self._lay, factors, self.a_diag, self.a_off, 1.0 / self.eps**2,
+                                        int(self.nu), [r.flat for r in rhs], [x.flat for x in xs], self.newton_tol,
+                                        self.newton_maxiter, self.lin_tol, self.lin_maxiter, self.inexact_linear_ratio,
+                                        work, counters)
+
+    def _count_newton(self, counters):
+        self._counters[0:2] += counters  # work_counters['newton'], ['linear'] (AllenCahn_2D_FD.py:188,194)
+        self._counters[6:7] += counters[0:1]  # newton_itercount (:203)
 
     def solve_system(self, rhs, factor, u0, t):
         me = self.dtype_u(u0)
@@ -516,15 +532,50 @@ class AllenCahnSemiMixin(AllenCahnMixin):
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, counters.clone()))
-        self._counters[1:2] += counters.sum(dtype=torch.int32)  # work_counters['linear'] (AllenCahn_2D_FD.py:327-331)
+        total = counters.sum(dtype=torch.int32)
+        self._counters[1:2] += total  # work_counters['linear'] (AllenCahn_2D_FD.py:327-331)
+        self._counters[7:8] += total  # lin_itercount (:348)
         self.lin_ncalls += B
+
+
+class AllenCahnSemiV2Mixin(AllenCahnMixin):
+    """``allencahn_semiimplicit_v2`` (AllenCahn_2D_FD.py:380-484): ``Delta u - u^(nu+1)/eps^2`` implicit - the batched
+    Newton kernel with the Jacobian of that part; the inner CG runs to ``lin_tol`` with scipy's default iteration cap of
+    ten times the system size and the reference counts neither its iterations nor the Newton steps in ``work_counters``
+    (only ``newton_itercount`` / ``newton_ncalls``, :481-482) -, ``u/eps^2`` explicit."""
+
+    dtype_f = imex_mesh
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import imex_1st_order
+
+        return imex_1st_order
+
+    def _rhs_total(self, f):
+        return f.impl + f.expl
+
+    def eval_f_batch(self, us, ts, fs):  # :402-424 (no work counter there)
+        self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
+                                  [u.flat for u in us], [f.impl.flat for f in fs], [f.expl.flat for f in fs], split=2)
+
+    def _newton_launch(self, factors, rhs, xs, work, counters):
+        n = self.nvars[0] * self.nvars[1]
+        self._be.allencahn_newton_solve(self._lay, factors, self.a_diag, self.a_off, 1.0 / self.eps**2,
+                                        int(self.nu), [r.flat for r in rhs], [x.flat for x in xs], self.newton_tol,
+                                        self.newton_maxiter, self.lin_tol, min(10 * n, 2**31 - 1), None, work, counters,
+                                        variant=1)
+
+    def _count_newton(self, counters):
+        self._counters[6:7] += counters[0:1]
 
 
 def _bind(base):
     """Concrete problem classes over a given ``Problem`` base class."""
     ns = {}
     for name, mixin in (("heatNd_unforced", HeatMixin), ("heatNd_forced", HeatForcedMixin),
-                        ("allencahn_fullyimplicit", AllenCahnMixin), ("allencahn_semiimplicit", AllenCahnSemiMixin)):
+                        ("allencahn_fullyimplicit", AllenCahnMixin), ("allencahn_semiimplicit", AllenCahnSemiMixin),
+                        ("allencahn_semiimplicit_v2", AllenCahnSemiV2Mixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
     return ns
 

@@ -259,13 +259,16 @@ class NumpyBackend:
             if profile is not None:
                 self._grid(lay, fexpls[i])[...] = self._grid(lay, profile) * gts[i]
 
-    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None):
+    def allencahn_eval_f(self, lay, a_diag, a_off, inv_eps2, nu_exp, us, fs, fexpls=None, split=None):
         self.launches += 1
         for i, (u, f) in enumerate(zip(us, fs)):
             x = self._grid(lay, u)
             lap = a_diag * x + a_off * self._lap_sum(x, True)
             react = inv_eps2 * x * (1.0 - x**nu_exp)
-            if fexpls is None:
+            if split == 2:
+                self._grid(lay, f)[...] = lap - inv_eps2 * x ** (nu_exp + 1)
+                self._grid(lay, fexpls[i])[...] = inv_eps2 * x
+            elif fexpls is None:
                 self._grid(lay, f)[...] = lap + react
             else:
                 self._grid(lay, f)[...] = lap
@@ -350,20 +353,27 @@ class NumpyBackend:
             self._grid(lay, x)[...] = np.linalg.solve(Mx, self._grid(lay, r))
 
     def allencahn_newton_solve(self, lay, factors, a_diag, a_off, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter,
-                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev):
+                               lin_tol, lin_maxiter, inexact_ratio, work, counters_dev, variant=0):
         self.launches += 1
         for factor, r, u in zip(factors, rhs, us):
             x = self._grid(lay, u)
             b = self._grid(lay, r)
             n, tol = 0, lin_tol
             while n < newton_maxiter:
-                g = x - factor * (a_diag * x + a_off * self._lap_sum(x, True) + inv_eps2 * x * (1.0 - x**nu_exp)) - b
+                lap = a_diag * x + a_off * self._lap_sum(x, True)
+                if variant == 0:
+                    g = x - factor * (lap + inv_eps2 * x * (1.0 - x**nu_exp)) - b
+                else:
+                    g = x - factor * (lap - inv_eps2 * x ** (nu_exp + 1)) - b
                 res = np.max(np.abs(g))
                 if inexact_ratio:
                     tol = res * inexact_ratio
                 if res < newton_tol:
                     break
-                d = 1.0 - factor * (a_diag + inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp))
+                if variant == 0:
+                    d = 1.0 - factor * (a_diag + inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp))
+                else:
+                    d = 1.0 - factor * (a_diag - inv_eps2 * ((nu_exp + 1) * x**nu_exp))
                 mv = lambda v: d * v - factor * a_off * self._lap_sum(v, True)  # noqa: E731
                 z = np.zeros_like(x)
                 counters_dev[1] += self._cg(mv, g, z, tol, lin_maxiter)

@@ -36,7 +36,8 @@ def classes():
 
     return ({"heatNd_unforced": problems.heatNd_unforced, "heatNd_forced": problems.heatNd_forced,
              "allencahn_fullyimplicit": problems.allencahn_fullyimplicit,
-             "allencahn_semiimplicit": problems.allencahn_semiimplicit},
+             "allencahn_semiimplicit": problems.allencahn_semiimplicit,
+             "allencahn_semiimplicit_v2": problems.allencahn_semiimplicit_v2},
             {"generic_implicit": sweepers.generic_implicit, "imex_1st_order": sweepers.imex_1st_order})
 
 
@@ -88,7 +89,10 @@ def check_operator(name):
     else:
         assert P.work_counters["newton"].niter == int(g.get("newton", 0))
         assert close_counts(P.work_counters["linear"].niter, int(g["linear"]))
-        assert P.work_counters["rhs"].niter == 1
+        v2 = spec["problem"].endswith("_v2")  # counts Newton steps in newton_itercount only, eval_f not at all
+        assert P.work_counters["rhs"].niter == (0 if v2 else 1)
+        if "newton_itercount" in g:
+            assert P.newton_itercount == int(g["newton_itercount"]) and P.newton_ncalls == 1
     t_ex = 0.0 if spec["problem"].startswith("allencahn") else 0.1
     assert relerr(P.u_exact(t_ex).get(), g["u_exact"]) == 0.0  # host numpy expression, then upload
 
@@ -243,6 +247,8 @@ def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
             keep = [i for i in range(len(want)) if i not in loose or niter[i] == g["niter"][i]]
             slack = 0.06 if name.startswith("run_config") else count_slack
             assert close_counts([got[i] for i in keep], [want[i] for i in keep], slack), (key, got, want)
+    if "newton_itercount" in g:  # the reference's plain-int totals (AllenCahn_2D_FD.py:202-203,481-482)
+        assert P.newton_itercount == int(g["newton_itercount"]) and P.newton_ncalls == int(g["newton_ncalls"])
     return dict(niter=niter, uend=uend, stats=stats)
 
 

@@ -23,6 +23,8 @@ def test_operator_vectors(oracle, name):
     else:
         assert P.counters["newton"].niter == int(g["newton"]) if "newton" in g else P.counters["newton"].niter == 0
         assert P.counters["linear"].niter == int(g["linear"])
+        if "newton_itercount" in g:
+            assert P.newton_itercount == int(g["newton_itercount"])
     t_ex = 0.0 if spec["problem"].startswith("allencahn") else 0.1
     assert _relerr(P.u_exact(t_ex), g["u_exact"]) == 0.0
 
