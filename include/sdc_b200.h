@@ -198,6 +198,26 @@ int sdcb200_heat_cg_solve_ho(int ndim, int n, int bc, int order, const double* c
                              double* const* x, double rtol, int maxiter, void* work, size_t work_bytes, int* iters_dev,
                              void* stream);
 
+/* ---- general finite-difference operators + GMRES ---------------------------------------------------------------------
+ * A = (Kronecker sum of ONE 1-D stencil) with offsets -h .. h (h <= 4): coef_host[k + h] is the coefficient of offset k,
+ * already scaled by coeff / dx^derivative - any stencil helpers/problem_helper.py:4-80 produces within that width
+ * (centred, upwind, forward, backward; first or second derivative).  Periodic wrap, or - dirichlet-zero - closure rows
+ * lo_host / hi_host = h x (2h+1) as above (NULL on periodic grids).
+ *   sdcb200_fd_eval_f:     f_b = A u_b                      (GenericNDimFinDiff.eval_f, generic_ND_FD.py:188-206; the
+ *                                                            advection problems of AdvectionEquation_ND_FD.py)
+ *   sdcb200_fd_gmres_solve: (I - factor A) x = rhs by restarted GMRES exactly as the reference calls scipy's
+ *                           (generic_ND_FD.py:241-250: x0, rtol = lintol, maxiter = liniter counting INNER iterations
+ *                           - callback_type='legacy' -, atol = 0, restart = 20, no preconditioner); x: in = initial
+ *                           guess, out = solution; iters_dev[0] += inner iterations (= calls of the reference's work
+ *                           counter).  One persistent cooperative launch per solve.  work:
+ *                           sdcb200_fd_gmres_workspace_bytes(ndim, n, restart) bytes, 256-byte aligned.              */
+int sdcb200_fd_eval_f(int ndim, int n, int bc, int h, const double* coef_host, const double* lo_host,
+                      const double* hi_host, int B, const double* const* u, double* const* f, void* stream);
+size_t sdcb200_fd_gmres_workspace_bytes(int ndim, int n, int restart);
+int sdcb200_fd_gmres_solve(int ndim, int n, int bc, int h, const double* coef_host, const double* lo_host,
+                           const double* hi_host, double factor, const double* rhs, double* x, double rtol, int maxiter,
+                           int restart, void* work, size_t work_bytes, int* iters_dev, void* stream);
+
 /* ---- K4: Allen-Cahn Newton ------------------------------------------------------------------------------------------
  * Newton iteration with inner CG on the Jacobian for B node systems  u_b - factor_b (A u_b + 1/eps^2 u_b (1 - u_b^nu)) =
  * rhs_b, whole solve in one persistent launch (allencahn_fullyimplicit.solve_system, AllenCahn_2D_FD.py:137-205; B > 1:

@@ -31,12 +31,13 @@ from pySDC.implementations.controller_classes.controller_nonMPI import controlle
 from pySDC.implementations.hooks.log_work import LogWork  # noqa: E402
 from pySDC.implementations.problem_classes.AllenCahn_2D_FD import (  # noqa: E402
     allencahn_fullyimplicit, allencahn_semiimplicit, allencahn_semiimplicit_v2)
+from pySDC.implementations.problem_classes.AdvectionEquation_ND_FD import advectionNd  # noqa: E402
 from pySDC.implementations.problem_classes.HeatEquation_ND_FD import heatNd_forced, heatNd_unforced  # noqa: E402
 from pySDC.implementations.sweeper_classes.generic_implicit import generic_implicit  # noqa: E402
 from pySDC.implementations.sweeper_classes.imex_1st_order import imex_1st_order  # noqa: E402
 from pySDC.implementations.transfer_classes.TransferMesh import mesh_to_mesh  # noqa: E402
 
-PROBLEMS = {"heatNd_unforced": heatNd_unforced, "heatNd_forced": heatNd_forced,
+PROBLEMS = {"heatNd_unforced": heatNd_unforced, "heatNd_forced": heatNd_forced, "advectionNd": advectionNd,
             "allencahn_fullyimplicit": allencahn_fullyimplicit, "allencahn_semiimplicit": allencahn_semiimplicit,
             "allencahn_semiimplicit_v2": allencahn_semiimplicit_v2}
 SWEEPERS = {"generic_implicit": generic_implicit, "imex_1st_order": imex_1st_order}
@@ -81,6 +82,68 @@ def make_description(spec):
         "step_params": dict(spec["step_params"]),
     }
     return d
+
+
+def gmres_fixtures():
+    """solver_type='GMRES' (generic_ND_FD.py:241-250) and advectionNd (AdvectionEquation_ND_FD.py): operator vectors for
+    every stencil family of helpers/problem_helper.py:4-39 and short SDC runs modelled on tutorial/step_5/C and
+    step_8/C (the latter with its cap of 10 GMRES iterations per solve)."""
+    for tag, cls, pp in [
+        ("advection1d_center_o2", advectionNd, dict(nvars=64, c=1.0, freq=2, stencil_type="center", order=2, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection1d_upwind_o5", advectionNd, dict(nvars=64, c=0.7, freq=4, stencil_type="upwind", order=5, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection1d_upwind_o1", advectionNd, dict(nvars=128, c=1.0, freq=2, stencil_type="upwind", order=1, bc="periodic", solver_type="GMRES", lintol=1e-10)),
+        ("advection1d_forward_o3", advectionNd, dict(nvars=64, c=-1.0, freq=2, stencil_type="forward", order=3, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection2d_center_o6", advectionNd, dict(nvars=(32, 32), c=0.1, freq=(2, 2), stencil_type="center", order=6, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection2d_backward_o2", advectionNd, dict(nvars=(32, 32), c=1.0, freq=(2, 4), stencil_type="backward", order=2, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection3d_upwind_o3", advectionNd, dict(nvars=(16, 16, 16), c=0.5, freq=(2, 2, 2), stencil_type="upwind", order=3, bc="periodic", solver_type="GMRES", lintol=1e-12)),
+        ("advection2d_dirichlet_center_o4", advectionNd, dict(nvars=(31, 31), c=1.0, freq=(1, 2), stencil_type="center", order=4, bc="dirichlet-zero", solver_type="GMRES", lintol=1e-12)),
+        ("advection1d_dirichlet_upwind_o4", advectionNd, dict(nvars=63, c=1.0, freq=3, stencil_type="upwind", order=4, bc="dirichlet-zero", solver_type="GMRES", lintol=1e-12)),
+        ("heat2d_dirichlet_gmres", heatNd_unforced, dict(nvars=(31, 31), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="GMRES", lintol=1e-12)),
+        ("heat2d_periodic_o4_gmres", heatNd_forced, dict(nvars=(32, 32), nu=0.1, freq=(2, 2), bc="periodic", order=4, solver_type="GMRES", lintol=1e-12)),
+        ("heat3d_dirichlet_o6_gmres", heatNd_unforced, dict(nvars=(15, 15, 15), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero", order=6, solver_type="GMRES", lintol=1e-12)),
+        ("heat1d_dirichlet_gmres_capped", heatNd_unforced, dict(nvars=127, nu=0.7, freq=2, bc="dirichlet-zero", solver_type="GMRES", lintol=1e-13, liniter=33)),
+    ]:
+        P = cls(**pp)
+        gen = np.random.default_rng(sum(map(ord, tag)))
+        u = P.u_init
+        u[:] = gen.standard_normal(u.shape)
+        rhs = P.u_init
+        rhs[:] = gen.standard_normal(u.shape)
+        t, factor = 0.37, 0.0123
+        f = P.eval_f(u, t)
+        sol = P.solve_system(rhs, factor, u, t)
+        spec = dict(problem=cls.__name__, problem_params=_jsonable(pp), t=t, factor=factor)
+        save("op_" + tag, spec, u=np.asarray(u), rhs=np.asarray(rhs), f=np.asarray(f), sol=np.asarray(sol),
+             gmres_iters=np.array(P.work_counters["GMRES"].niter), u_exact=np.asarray(P.u_exact(0.1)))
+        print("   GMRES iterations:", P.work_counters["GMRES"].niter)
+    # tutorial/step_5/C_advection_and_PFASST.py:17-35 on one level, with GMRES instead of the sparse direct solve
+    spec = dict(problem="advectionNd", sweeper="generic_implicit",
+                problem_params=dict(nvars=128, c=1, freq=4, order=4, bc="periodic", stencil_type="center",
+                                    solver_type="GMRES", lintol=1e-12),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+                level_params=dict(dt=0.0625, restol=1e-9), step_params=dict(maxiter=50), t0=0.0, Tend=0.25, u0="exact")
+    run_case("run_advection1d_gi_lu_gmres_128", spec)
+    # tutorial/step_8/C_iteration_estimator.py:85-107: 2-D, order 6, at most 10 GMRES iterations per solve
+    spec = dict(problem="advectionNd", sweeper="generic_implicit",
+                problem_params=dict(nvars=[64, 64], c=0.1, freq=[2, 2], order=6, bc="periodic", stencil_type="center",
+                                    solver_type="GMRES", liniter=10),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+                level_params=dict(dt=0.05, restol=1e-9), step_params=dict(maxiter=50), t0=0.0, Tend=0.1, u0="exact")
+    run_case("run_advection2d_gi_lu_gmres10_64", spec)
+    # upwind stencil with a diagonal QDelta
+    spec = dict(problem="advectionNd", sweeper="generic_implicit",
+                problem_params=dict(nvars=[32, 32, 32], c=1.0, freq=[2, 2, 2], order=3, bc="periodic",
+                                    stencil_type="upwind", solver_type="GMRES", lintol=1e-12),
+                sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="MIN-SR-NS"),
+                level_params=dict(dt=0.01, restol=1e-9), step_params=dict(maxiter=50), t0=0.0, Tend=0.02, u0="exact")
+    run_case("run_advection3d_gi_minsrns_gmres_32", spec)
+    # heat equation on GMRES
+    spec = dict(problem="heatNd_forced", sweeper="imex_1st_order",
+                problem_params=dict(nvars=[63, 63], nu=0.1, freq=[4, 4], bc="dirichlet-zero", solver_type="GMRES",
+                                    lintol=1e-12, liniter=10000),
+                sweeper_params=dict(num_nodes=4, quad_type="RADAU-RIGHT", QI="LU"),
+                level_params=dict(dt=0.1, restol=1e-10), step_params=dict(maxiter=50), t0=0.0, Tend=0.2, u0="exact")
+    run_case("run_heat2d_imex_lu_gmres_63", spec)
 
 
 def allencahn_semiimplicit_v2_fixtures():
@@ -503,7 +566,7 @@ def pfasst_config5():
     print("  PFASST config 5", niter, "wall", wall)
 
 
-FAMILIES = {"allencahn_semi_v2": allencahn_semiimplicit_v2_fixtures, "allencahn_semi": allencahn_semiimplicit_fixtures, "runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "transfer": transfer_vectors,
+FAMILIES = {"gmres": gmres_fixtures, "allencahn_semi_v2": allencahn_semiimplicit_v2_fixtures, "allencahn_semi": allencahn_semiimplicit_fixtures, "runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "transfer": transfer_vectors,
             "pfasst": pfasst_runs,
             "pfasst_config5": pfasst_config5}
 

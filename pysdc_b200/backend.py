@@ -59,6 +59,10 @@ def _declare(lib):
         "sdcb200_cg_ho_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
         "sdcb200_heat_cg_solve_ho": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_int, PD, PP, PP, c_d, c_int, _c_dp,
                                              c_sz, _c_dp, _c_dp]),
+        "sdcb200_fd_eval_f": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_int, PP, PP, _c_dp]),
+        "sdcb200_fd_gmres_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+        "sdcb200_fd_gmres_solve": (c_int, [c_int, c_int, c_int, c_int, PD, PD, PD, c_d, _c_dp, _c_dp, c_d, c_int, c_int,
+                                           _c_dp, c_sz, _c_dp, _c_dp]),
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int, c_int]),
         "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
                                                    c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
@@ -234,6 +238,32 @@ class CudaBackend:
         self._check(self.lib.sdcb200_heat_cg_solve_ho(
             lay.ndim, lay.n, bc, op["order"], c, lo, hi, len(xs), _dbl_array(factors), _ptr_array(rhs), _ptr_array(xs),
             float(rtol), int(maxiter), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
+
+    # -- general finite-difference operators, GMRES (gmres.cu) ---------------------------------------------------------
+    @staticmethod
+    def _fd_tables(op):
+        lo = None if op["lo"] is None else _dbl_array(np.asarray(op["lo"], dtype=np.float64).ravel())
+        hi = None if op["hi"] is None else _dbl_array(np.asarray(op["hi"], dtype=np.float64).ravel())
+        return _dbl_array(op["coef"]), lo, hi
+
+    def fd_eval_f(self, lay, bc, op, us, fs):
+        """fs[i] = A us[i] for the operator tables of problems.fd_operator_tables."""
+        self.launches += 1
+        c, lo, hi = self._fd_tables(op)
+        self._check(self.lib.sdcb200_fd_eval_f(lay.ndim, lay.n, bc, op["h"], c, lo, hi, len(us), _ptr_array(us),
+                                               _ptr_array(fs), self._stream()))
+
+    def fd_gmres_workspace(self, lay, restart):
+        nbytes = self.lib.sdcb200_fd_gmres_workspace_bytes(lay.ndim, lay.n, restart)
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def fd_gmres_solve(self, lay, bc, op, factor, rhs, x, rtol, maxiter, restart, work, iters_dev):
+        """(I - factor A) x = rhs by restarted GMRES in one persistent launch, in place on x (initial guess in)."""
+        self.launches += 1
+        c, lo, hi = self._fd_tables(op)
+        self._check(self.lib.sdcb200_fd_gmres_solve(
+            lay.ndim, lay.n, bc, op["h"], c, lo, hi, float(factor), rhs.data_ptr(), x.data_ptr(), float(rtol),
+            int(maxiter), int(restart), work.data_ptr(), work.numel() * 8, iters_dev.data_ptr(), self._stream()))
 
     # -- slab-decomposed solves over peer-mapped memory -----------------------------------------------------------------
     def slab_cg_workspace(self, lay, comm, B):

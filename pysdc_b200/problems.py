@@ -22,6 +22,7 @@ from .errors import ProblemError
 from .fields_io import OutputMixin
 
 BC_CODES = {"dirichlet-zero": 0, "periodic": 1}
+GMRES_RESTART = 20  # scipy's default restart length, the only one the reference uses (generic_ND_FD.py:241-250)
 
 
 def grid_1d(size, bc, left=0.0, right=1.0):
@@ -76,6 +77,86 @@ def high_order_tables(order, bc, scale):
     return tables
 
 
+def fd_steps(derivative, order, stencil_type):
+    """Offsets of the stencil (helpers/problem_helper.py:4-39)."""
+    if stencil_type == "center":
+        n = order + derivative - (derivative + 1) % 2 // 1
+        return np.arange(n) - n // 2
+    if stencil_type == "forward":
+        return np.arange(order + derivative)
+    if stencil_type == "backward":
+        return -np.arange(order + derivative)
+    if stencil_type == "upwind":
+        n = order + derivative
+        return -np.arange(n) if n <= 3 else np.append(-np.arange(n - 1)[::-1], [1])
+    raise ValueError(f'Stencil must be of type "center", "forward", "backward" or "upwind", not {stencil_type}.')
+
+
+def fd_operator_tables(derivative, order, stencil_type, bc, dx, coeff):
+    """The 1-D operator ``coeff * d^derivative/dx^derivative`` of the reference (helpers/problem_helper.py:83-242,
+    generic_ND_FD.py:140-149) as what the device needs: half width ``h``, ``coef[k + h]`` = coefficient of offset k, and
+    on dirichlet-zero grids the first / last h rows of the matrix (``lo[i]``: row i on columns 0 .. 2h; ``hi[i]``: row
+    n-1-i on the last 2h+1 columns), which hold the reference's one-sided closure stencils (default ``reduce=False``;
+    the coefficient of the zero boundary value drops out) and, where a one-sided stencil needs no closure on that side,
+    the truncated interior stencil."""
+    w, steps = fd_weights(derivative, fd_steps(derivative, order, stencil_type))
+    h = int(max(-steps.min(), steps.max()))
+    scale = lambda v: (np.asarray(v, dtype=float) / dx**derivative) * coeff  # noqa: E731  (the reference's order)
+    coef = np.zeros(2 * h + 1)
+    coef[steps + h] = w
+    tables = dict(h=h, coef=scale(coef), lo=None, hi=None)
+    if bc != "periodic":
+        m = 4 * h + 2  # any size with the two boundary blocks apart gives the same rows
+        A = np.zeros((m, m))
+        for c, k in zip(w, steps):
+            A += c * np.eye(m, k=int(k))
+        for side, width in ((0, int(-steps.min())), (1, int(steps.max()))):
+            for i in range(width):
+                if side == 0:
+                    bw, _ = fd_weights(derivative, np.arange(-(i + 1), order + derivative - (i + 1)))
+                    A[i, :] = 0.0
+                    A[i, : len(bw) - 1] = bw[1:]
+                else:
+                    bw, _ = fd_weights(derivative, np.arange(-(order + derivative) + (i + 2), (i + 2)))
+                    A[-i - 1, :] = 0.0
+                    A[-i - 1, -len(bw) + 1:] = bw[:-1]
+        if order + derivative - 1 > 2 * h + 1:
+            raise ProblemError("closure rows wider than the device stencil tables")
+        tables.update(lo=scale(A[:h, : 2 * h + 1]), hi=scale(A[::-1][:h, -(2 * h + 1):]))
+    return tables
+
+
+def check_fd_params(nvars, freq, bc):
+    """Parameter checks of GenericNDimFinDiff (generic_ND_FD.py:99-133); returns (nvars, freq, ndim, bc)."""
+    if type(nvars) not in [int, tuple]:
+        raise ProblemError("nvars should be either tuple or int")
+    if type(freq) not in [int, tuple]:
+        raise ProblemError("freq should be either tuple or int")
+    if type(nvars) is int:
+        nvars = (nvars,)
+    ndim = len(nvars)
+    if ndim > 3:
+        raise ProblemError(f"can work with up to three dimensions, got {ndim}")
+    if type(freq) is int:
+        freq = (freq,) * ndim
+    if len(freq) != ndim:
+        raise ProblemError(f"len(freq)={len(freq)}, different to ndim={ndim}")
+    for f in freq:
+        if ndim == 1 and f == -1:
+            bc = "periodic"
+            break
+        if f % 2 != 0 and bc == "periodic":
+            raise ProblemError("need even number of frequencies due to periodic BCs")
+    for nvar in nvars:
+        if nvar % 2 != 0 and bc == "periodic":
+            raise ProblemError("the setup requires nvars = 2^p per dimension")
+        if (nvar + 1) % 2 != 0 and bc == "dirichlet-zero":
+            raise ProblemError("setup requires nvars = 2^p - 1")
+    if ndim > 1 and nvars[1:] != nvars[:-1]:
+        raise ProblemError("need a square domain, got %s" % (nvars,))
+    return nvars, freq, ndim, bc
+
+
 class DeviceWorkCounter:
     """``WorkCounter`` (core/problem.py:16-40) whose count lives in a device int: the solver kernels add their
     iteration counts without a host round trip; reading ``niter`` synchronises."""
@@ -114,32 +195,7 @@ class HeatMixin(OutputMixin):
         # Chebyshev polynomial of the operator: same stopping test and tolerance as the reference's plain CG, about
         # half the iterations (work_counters['CG'] then counts preconditioned iterations).
         # parameter checks of generic_ND_FD.py:99-133
-        if type(nvars) not in [int, tuple]:
-            raise ProblemError("nvars should be either tuple or int")
-        if type(freq) not in [int, tuple]:
-            raise ProblemError("freq should be either tuple or int")
-        if type(nvars) is int:
-            nvars = (nvars,)
-        ndim = len(nvars)
-        if ndim > 3:
-            raise ProblemError(f"can work with up to three dimensions, got {ndim}")
-        if type(freq) is int:
-            freq = (freq,) * ndim
-        if len(freq) != ndim:
-            raise ProblemError(f"len(freq)={len(freq)}, different to ndim={ndim}")
-        for f in freq:
-            if ndim == 1 and f == -1:
-                bc = "periodic"
-                break
-            if f % 2 != 0 and bc == "periodic":
-                raise ProblemError("need even number of frequencies due to periodic BCs")
-        for nvar in nvars:
-            if nvar % 2 != 0 and bc == "periodic":
-                raise ProblemError("the setup requires nvars = 2^p per dimension")
-            if (nvar + 1) % 2 != 0 and bc == "dirichlet-zero":
-                raise ProblemError("setup requires nvars = 2^p - 1")
-        if ndim > 1 and nvars[1:] != nvars[:-1]:
-            raise ProblemError("need a square domain, got %s" % (nvars,))
+        nvars, freq, ndim, bc = check_fd_params(nvars, freq, bc)
         # what the device path implements
         if bc not in BC_CODES:
             raise ProblemError(f"boundary condition {bc!r} is not implemented on the device (have {list(BC_CODES)})")
@@ -147,11 +203,15 @@ class HeatMixin(OutputMixin):
             raise ProblemError("the device stencils are the centred Laplacians of order 2, 4, 6 and 8; "
                                f"got order={order}, stencil_type={stencil_type!r}")
         if order != 2 and (solver_type == "direct" or preconditioner is not None or comm is not None):
-            raise ProblemError("order > 2 is implemented with solver_type='CG', without preconditioner and on one GPU")
+            raise ProblemError("order > 2 is implemented with solver_type='CG' or 'GMRES', without preconditioner and "
+                               "on one GPU")
         if order != 2 and any(nv <= order for nv in nvars):
             raise ProblemError(f"grid too small for the order-{order} stencil")
-        if solver_type not in ("CG", "direct"):
-            raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device (have 'CG', 'direct')")
+        if solver_type not in ("CG", "GMRES", "direct"):
+            raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device (have 'CG', 'GMRES', "
+                               "'direct')")
+        if solver_type == "GMRES" and (preconditioner is not None or comm is not None):
+            raise ProblemError("solver_type='GMRES' runs without preconditioner and on one GPU")
         if solver_type == "direct" and ndim > 1:
             raise ProblemError("solver_type='direct' is implemented on the device for 1-D grids only; use 'CG'")
 
@@ -182,6 +242,8 @@ class HeatMixin(OutputMixin):
         self._ho = None if order == 2 else high_order_tables(order, bc, (1.0 / dx**2) * nu)
         if self._ho is not None:
             self.a_diag = ndim * self._ho["centre"][0]
+        # GMRES runs on the general operator tables (gmres.cu), whatever the order
+        self._fd = fd_operator_tables(2, order, stencil_type, bc, dx, nu) if solver_type == "GMRES" else None
         self._precond = 1 if preconditioner == "chebyshev" else 0
         self._comm = comm if slab else None
         self._lay = comm.slab_layout(nvars) if slab else get_layout(nvars)
@@ -259,7 +321,9 @@ class HeatMixin(OutputMixin):
     # -- implicit solves ----------------------------------------------------------------------------------------------
     def _cg_work(self, B):
         if B not in self._work:
-            if self._ho is not None:
+            if self.solver_type == "GMRES":
+                self._work[B] = self._be.fd_gmres_workspace(self._lay, GMRES_RESTART)
+            elif self._ho is not None:
                 self._work[B] = self._be.cg_ho_workspace(self._lay, B)
             elif self._comm is not None:
                 import weakref
@@ -286,7 +350,12 @@ class HeatMixin(OutputMixin):
         if log is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        if self._ho is not None:
+        if self.solver_type == "GMRES":  # generic_ND_FD.py:241-250: one restarted-GMRES launch per system
+            work = self._cg_work(1)
+            for i, (f, r, x) in enumerate(zip(factors, rhs, xs)):
+                self._be.fd_gmres_solve(self._lay, self._bc, self._fd, f, r.flat, x.flat, self.lintol, self.liniter,
+                                        GMRES_RESTART, work, counters[i: i + 1])
+        elif self._ho is not None:
             self._be.heat_cg_solve_ho(self._lay, self._bc, self._ho, list(factors), [r.flat for r in rhs],
                                       [x.flat for x in xs], self.lintol, self.liniter, self._cg_work(len(xs)), counters)
         elif self._comm is not None:
@@ -354,6 +423,102 @@ class HeatForcedMixin(HeatMixin):
         from .sweepers import imex_1st_order
 
         return imex_1st_order
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# advection equation
+# ---------------------------------------------------------------------------------------------------------------------
+class AdvectionMixin(OutputMixin):
+    """``advectionNd`` (problem_classes/AdvectionEquation_ND_FD.py:7-164 on top of ``GenericNDimFinDiff``): u_t = -c
+    grad u in 1-3 dimensions, any stencil of helpers/problem_helper.py:4-39 within four grid points (centred order 2-8,
+    upwind order 1-5, forward / backward order 1-4), ``eval_f`` by the general finite-difference kernel and the node
+    solves by the device GMRES (``solver_type='GMRES'``; the non-symmetric systems have no device 'direct' or 'CG'
+    path)."""
+
+    dtype_u = mesh
+    dtype_f = mesh
+    forced = False
+
+    def __init__(self, nvars=512, c=1.0, freq=2, stencil_type="center", order=2, lintol=1e-12, liniter=10000,
+                 solver_type="direct", bc="periodic", sigma=6e-2):
+        nvars, freq, ndim, bc = check_fd_params(nvars, freq, bc)
+        if bc not in BC_CODES:
+            raise ProblemError(f"boundary condition {bc!r} is not implemented on the device (have {list(BC_CODES)})")
+        if solver_type != "GMRES":
+            raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device for the advection "
+                               "equation: its systems are non-symmetric, use solver_type='GMRES'")
+        try:
+            steps = fd_steps(1, order, stencil_type)
+        except ValueError as e:
+            raise ProblemError(str(e)) from None
+        if max(-steps.min(), steps.max()) > 4 or order < 1:
+            raise ProblemError(f"the device stencils reach at most four grid points; got order={order}, "
+                               f"stencil_type={stencil_type!r}")
+        if any(nv <= 2 * max(-steps.min(), steps.max()) for nv in nvars):
+            raise ProblemError(f"grid too small for the order-{order} stencil")
+        super().__init__(init=(nvars[0] if ndim == 1 else nvars, None, np.dtype("float64")))
+        dx, xvalues = grid_1d(nvars[0], bc)
+        self.xvalues = xvalues
+        self._makeAttributeAndRegister("nvars", "stencil_type", "order", "bc", localVars=locals(), readOnly=True)
+        self._makeAttributeAndRegister("freq", "lintol", "liniter", "solver_type", localVars=locals())
+        self._makeAttributeAndRegister("c", localVars=locals(), readOnly=True)
+        self._makeAttributeAndRegister("sigma", localVars=locals())
+        self._bc = BC_CODES[bc]
+        self._be = get_backend()
+        self._lay = get_layout(nvars)
+        self._fd = fd_operator_tables(1, order, stencil_type, bc, dx, -c)  # AdvectionEquation_ND_FD.py:89: coeff = -c
+        self._counters = self._be.zeros(2, dtype=torch.int32)  # [total GMRES its, its of the current solve]
+        self._work = None
+        self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
+
+    ndim = HeatMixin.ndim
+    dx = HeatMixin.dx
+    grids = HeatMixin.grids
+    get_default_sweeper_class = HeatMixin.get_default_sweeper_class
+
+    def eval_f_batch(self, us, ts, fs):
+        self._be.fd_eval_f(self._lay, self._bc, self._fd, [u.flat for u in us], [f.flat for f in fs])
+
+    def eval_f(self, u, t):
+        """generic_ND_FD.py:188-206."""
+        f = self.f_init
+        self.eval_f_batch([u], [t], [f])
+        return f
+
+    def solve_system_batch(self, rhs, factors, xs, ts=None):
+        """(I - factors[i] A) xs[i] = rhs[i] in place by restarted GMRES (generic_ND_FD.py:241-250), one persistent
+        launch per system."""
+        if self._work is None:
+            self._work = self._be.fd_gmres_workspace(self._lay, GMRES_RESTART)
+        counter = self._counters[1:2]
+        for f, r, x in zip(factors, rhs, xs):
+            self._be.fd_gmres_solve(self._lay, self._bc, self._fd, f, r.flat, x.flat, self.lintol, self.liniter,
+                                    GMRES_RESTART, self._work, counter)
+        self._counters[0:1] += counter
+        counter.zero_()
+
+    def solve_system(self, rhs, factor, u0, t):
+        sol = self.dtype_u(u0)
+        self.solve_system_batch([rhs], [factor], [sol], [t])
+        return sol
+
+    def u_exact(self, t, **kwargs):
+        """AdvectionEquation_ND_FD.py:95-141."""
+        ndim, freq, c, sigma, sol = self.ndim, self.freq, self.c, self.sigma, self.u_init
+        if ndim == 1:
+            x = self.grids
+            if freq[0] >= 0:
+                sol[:] = np.sin(np.pi * freq[0] * (x - c * t))
+            elif freq[0] == -1:
+                sol[:] = np.exp(-0.5 * (((x - (c * t)) % 1.0 - 0.5) / sigma) ** 2)
+        elif ndim == 2:
+            x, y = self.grids
+            sol[:] = np.sin(np.pi * freq[0] * (x - c * t)) * np.sin(np.pi * freq[1] * (y - c * t))
+        else:
+            x, y, z = self.grids
+            sol[:] = (np.sin(np.pi * freq[0] * (x - c * t)) * np.sin(np.pi * freq[1] * (y - c * t))
+                      * np.sin(np.pi * freq[2] * (z - c * t)))
+        return sol
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -574,6 +739,7 @@ def _bind(base):
     """Concrete problem classes over a given ``Problem`` base class."""
     ns = {}
     for name, mixin in (("heatNd_unforced", HeatMixin), ("heatNd_forced", HeatForcedMixin),
+                        ("advectionNd", AdvectionMixin),
                         ("allencahn_fullyimplicit", AllenCahnMixin), ("allencahn_semiimplicit", AllenCahnSemiMixin),
                         ("allencahn_semiimplicit_v2", AllenCahnSemiV2Mixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})

@@ -195,6 +195,134 @@ class NumpyBackend:
     def cg_ho_workspace(self, lay, B):
         return None
 
+    # ---- general finite-difference operators, GMRES -------------------------------------------------------------------
+    @staticmethod
+    def _fd_matrix(op, n, periodic):
+        h = op["h"]
+        A = np.zeros((n, n))
+        for i in range(n):
+            for k in range(-h, h + 1):
+                j = i + k
+                if periodic:
+                    A[i, j % n] += op["coef"][k + h]
+                elif 0 <= j < n:
+                    A[i, j] += op["coef"][k + h]
+        if not periodic:
+            w = 2 * h + 1
+            for i in range(h):
+                A[i, :] = 0.0
+                A[i, :w] = op["lo"][i]
+                A[n - 1 - i, :] = 0.0
+                A[n - 1 - i, n - w:] = op["hi"][i]
+        return A
+
+    def _fd_apply(self, op, lay, bc, x):
+        A = self._fd_matrix(op, lay.n, bc == 1)
+        out = np.zeros_like(x)
+        for ax in range(x.ndim):
+            out += np.moveaxis(np.tensordot(A, x, axes=([1], [ax])), 0, ax)
+        return out
+
+    def fd_eval_f(self, lay, bc, op, us, fs):
+        self.launches += 1
+        for u, f in zip(us, fs):
+            self._grid(lay, f)[...] = self._fd_apply(op, lay, bc, self._grid(lay, u))
+
+    def fd_gmres_workspace(self, lay, restart):
+        return None
+
+    @staticmethod
+    def _lartg(f, g):
+        """LAPACK dlartg as restated in csrc/gmres.cu (unscaled branch)."""
+        if g == 0.0:
+            return 1.0, 0.0, f
+        if f == 0.0:
+            return 0.0, np.copysign(1.0, g), abs(g)
+        d = np.sqrt(f * f + g * g)
+        r = np.copysign(d, f)
+        return abs(f) / d, g / r, r
+
+    def fd_gmres_solve(self, lay, bc, op, factor, rhs, x, rtol, maxiter, restart, work, iters_dev):
+        """numpy mirror of csrc/gmres.cu::fd_gmres_kernel, statement by statement (same fused Gram-Schmidt passes, same
+        scalar arithmetic), so that the CPU suite checks the device recurrence against the reference's fixtures."""
+        self.launches += 1
+        xg, b = self._grid(lay, x), self._grid(lay, rhs)
+        eps = np.finfo(float).eps
+        Mv = lambda v: v - factor * self._fd_apply(op, lay, bc, v)  # noqa: E731
+        dot = lambda u, v: float(np.vdot(u, v))  # noqa: E731
+        bnrm2 = np.sqrt(dot(b, b))
+        if bnrm2 == 0.0:
+            xg[...] = b
+            return
+        atol = rtol * bnrm2
+        ptol_max_factor = 1.0
+        ptol = bnrm2 * min(ptol_max_factor, atol / bnrm2)
+        presid, inner_iter = 0.0, 0
+        V = np.zeros((restart + 1,) + xg.shape)
+        V[0] = b - Mv(xg)
+        rnorm = np.sqrt(dot(V[0], V[0]))
+        if rnorm < atol:
+            return
+        h = np.zeros((restart, restart + 1))
+        giv = np.zeros((restart, 2))
+        for iteration in range(maxiter):
+            V[0] *= 1.0 / rnorm
+            S = np.zeros(restart + 1)
+            S[0] = rnorm
+            breakdown = False
+            for col in range(restart):
+                w = V[col + 1]
+                w[...] = Mv(V[col])
+                h0 = np.sqrt(dot(w, w))
+                hprev = 0.0
+                for k in range(col + 1):
+                    if k > 0:
+                        w -= hprev * V[k - 1]
+                    hprev = dot(V[k], w)
+                    h[col, k] = hprev
+                w -= hprev * V[col]
+                h1 = np.sqrt(dot(w, w))
+                if h1 <= eps * h0:
+                    breakdown = True
+                else:
+                    w *= 1.0 / h1
+                h[col, col + 1] = 0.0 if breakdown else h1
+                for k in range(col):
+                    c, s_ = giv[k]
+                    n0, n1 = h[col, k], h[col, k + 1]
+                    h[col, k], h[col, k + 1] = c * n0 + s_ * n1, -s_ * n0 + c * n1
+                c, s_, mag = self._lartg(h[col, col], h[col, col + 1])
+                giv[col] = c, s_
+                h[col, col], h[col, col + 1] = mag, 0.0
+                tmp = -s_ * S[col]
+                S[col], S[col + 1] = c * S[col], tmp
+                presid = abs(tmp)
+                inner_iter += 1
+                if inner_iter == maxiter:
+                    break
+                if presid <= ptol or breakdown:
+                    break
+            if h[col, col] == 0.0:
+                S[col] = 0.0
+            y = S[: col + 1].copy()
+            for k in range(col, 0, -1):
+                if y[k] != 0.0:
+                    y[k] /= h[k, k]
+                    y[:k] -= y[k] * h[k, :k]
+            if y[0] != 0.0:
+                y[0] /= h[0, 0]
+            xg += np.tensordot(y, V[: col + 1], axes=1)
+            V[0] = b - Mv(xg)
+            rnorm = np.sqrt(dot(V[0], V[0]))
+            if inner_iter == maxiter or rnorm <= atol or breakdown:
+                break
+            if presid <= ptol:
+                ptol_max_factor = max(eps, 0.25 * ptol_max_factor)
+            else:
+                ptol_max_factor = min(1.0, 1.5 * ptol_max_factor)
+            ptol = presid * min(ptol_max_factor, atol / rnorm)
+        iters_dev[0] += inner_iter
+
     def heat_cg_solve_ho(self, lay, bc, op, factors, rhs, xs, rtol, maxiter, work, iters_dev):
         self.launches += 1
         for b, (r, x) in enumerate(zip(rhs, xs)):

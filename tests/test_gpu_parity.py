@@ -49,7 +49,9 @@ def test_run(name):
     # 1-D grids with CG are badly conditioned (kappa ~ 1e4..1e5): CG loses orthogonality and its iteration count depends
     # on rounding details at the 10-30 % level (scipy vs scipy-with-another-BLAS would differ as much); the graded
     # quantities - SDC iteration counts, residual histories, solution - are asserted as everywhere else
-    pc.check_run(name, count_slack=None if "heat1d" in name else 0.02)
+    # (restarted GMRES: the inner stop `presid <= ptol` with scipy's adaptive ptol moves by an iteration per restart
+    # cycle under rounding-level differences: 5 % band on the per-step totals)
+    pc.check_run(name, count_slack=None if "heat1d" in name else (0.05 if "gmres" in name else 0.02))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -305,6 +307,48 @@ def test_datatype_surface():
         f.nope
     # the walls of the layout stay zero under arithmetic (they are the Dirichlet boundary)
     assert float(a.vol.sum()) == float(arr.sum())
+
+
+@pytest.mark.parametrize("cls,pp", [
+    ("advectionNd", dict(nvars=(256, 256), c=1.0, freq=(2, 2), stencil_type="upwind", order=3, bc="periodic")),
+    ("advectionNd", dict(nvars=(130, 130), c=0.3, freq=(2, 4), stencil_type="center", order=8, bc="periodic")),
+    ("advectionNd", dict(nvars=(40, 40, 40), c=1.0, freq=(2, 2, 2), stencil_type="upwind", order=5, bc="periodic")),
+    ("advectionNd", dict(nvars=1024, c=1.0, freq=4, stencil_type="backward", order=1, bc="periodic")),
+    ("advectionNd", dict(nvars=(63, 63), c=1.0, freq=(1, 1), stencil_type="forward", order=2, bc="dirichlet-zero")),
+    ("heatNd_unforced", dict(nvars=(33, 33, 33), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero")),
+    ("heatNd_unforced", dict(nvars=(127, 127), nu=0.1, freq=(2, 2), bc="dirichlet-zero", order=8)),
+    ("heatNd_unforced", dict(nvars=(66, 66), nu=1.0, freq=(2, 2), bc="periodic", order=4)),
+])
+def test_gmres_against_oracle(oracle, cls, pp):
+    """solver_type='GMRES' (generic_ND_FD.py:241-250) on grids that are not multiples of anything: eval_f and the
+    restarted-GMRES solve against the oracle (scipy's gmres on the reference's sparse matrix), iteration counts included;
+    a capped solve (liniter reached) returns scipy's iterate."""
+    probs, _ = pc.classes()
+    pp = dict(pp, solver_type="GMRES", lintol=1e-11)
+    P, O = probs[cls](**pp), oracle.make_problem(cls, pp)
+    rng = np.random.default_rng(77)
+    u, rhs = rng.standard_normal(P.nvars), rng.standard_normal(P.nvars)
+    f = P.eval_f(pc.to_mesh(P, u), 0.0).get()
+    f_ref = O.eval_f(u, 0.0)
+    assert np.max(np.abs(f - f_ref)) <= pc.stencil_tol(P, np.max(np.abs(u)), f_ref)
+    factor = 0.004
+    sol = P.solve_system(pc.to_mesh(P, rhs), factor, pc.to_mesh(P, u), 0.0).get()
+    sol_ref = O.solve_system(rhs, factor, u, 0.0)
+    assert pc.relerr(sol, sol_ref) < pc.TOL_SOLVE
+    assert pc.close_counts(P.work_counters["GMRES"].niter, O.counters["GMRES"].niter, 0.05)
+    # zero right-hand side: scipy returns b; exact initial guess: no iteration
+    zero = P.solve_system(pc.to_mesh(P, 0 * rhs), factor, pc.to_mesh(P, u), 0.0).get()
+    assert not zero.any()
+    before = P.work_counters["GMRES"].niter
+    again = P.solve_system(pc.to_mesh(P, rhs), factor, pc.to_mesh(P, sol), 0.0).get()
+    assert pc.relerr(again, sol) < pc.TOL_SOLVE and P.work_counters["GMRES"].niter - before <= 2
+    # iteration cap (callback_type='legacy': liniter counts inner iterations)
+    P.liniter = O.liniter = 7
+    before, before_ref = P.work_counters["GMRES"].niter, O.counters["GMRES"].niter
+    capped = P.solve_system(pc.to_mesh(P, rhs), factor, pc.to_mesh(P, u), 0.0).get()
+    capped_ref = O.solve_system(rhs, factor, u, 0.0)
+    assert P.work_counters["GMRES"].niter - before == O.counters["GMRES"].niter - before_ref == 7
+    assert pc.relerr(capped, capped_ref) < 1e-9
 
 
 def test_allencahn_newton_against_oracle(oracle):

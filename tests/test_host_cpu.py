@@ -40,7 +40,9 @@ def test_sweep_dump(name):
 def test_run(name):
     # 1-D grids are badly conditioned (kappa ~ 1e4): CG loses orthogonality and its iteration count depends on
     # rounding details at the 10 % level; SDC iteration counts and the solution are unaffected
-    pc.check_run(name, count_slack=None if "heat1d" in name else 0.02)
+    # (restarted GMRES: the inner stop `presid <= ptol` with scipy's adaptive ptol moves by an iteration per restart
+    # cycle under rounding-level differences: 5 % band on the per-step totals)
+    pc.check_run(name, count_slack=None if "heat1d" in name else (0.05 if "gmres" in name else 0.02))
 
 
 def test_polynomial_preconditioner_host_semantics():

@@ -20,6 +20,8 @@ def test_operator_vectors(oracle, name):
     assert _relerr(sol, g["sol"]) == 0.0
     if "cg_iters" in g:
         assert P.counters["CG"].niter == int(g["cg_iters"])
+    elif "gmres_iters" in g:
+        assert P.counters["GMRES"].niter == int(g["gmres_iters"])
     else:
         assert P.counters["newton"].niter == int(g["newton"]) if "newton" in g else P.counters["newton"].niter == 0
         assert P.counters["linear"].niter == int(g["linear"])
