@@ -314,7 +314,8 @@ def test_datatype_surface():
     ("advectionNd", dict(nvars=(130, 130), c=0.3, freq=(2, 4), stencil_type="center", order=8, bc="periodic")),
     ("advectionNd", dict(nvars=(40, 40, 40), c=1.0, freq=(2, 2, 2), stencil_type="upwind", order=5, bc="periodic")),
     ("advectionNd", dict(nvars=1024, c=1.0, freq=4, stencil_type="backward", order=1, bc="periodic")),
-    ("advectionNd", dict(nvars=(63, 63), c=1.0, freq=(1, 1), stencil_type="forward", order=2, bc="dirichlet-zero")),
+    ("advectionNd", dict(nvars=(63, 63), c=1.0, freq=(1, 1), stencil_type="backward", order=2, bc="dirichlet-zero")),
+    ("advectionNd", dict(nvars=(31, 31, 31), c=1.0, freq=(1, 1, 1), stencil_type="upwind", order=3, bc="dirichlet-zero")),
     ("heatNd_unforced", dict(nvars=(33, 33, 33), nu=0.1, freq=(1, 1, 1), bc="dirichlet-zero")),
     ("heatNd_unforced", dict(nvars=(127, 127), nu=0.1, freq=(2, 2), bc="dirichlet-zero", order=8)),
     ("heatNd_unforced", dict(nvars=(66, 66), nu=1.0, freq=(2, 2), bc="periodic", order=4)),
