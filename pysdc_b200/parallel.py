@@ -236,6 +236,19 @@ class TorchComm:
         else:
             dist.broadcast(t, src=self._global(root), group=self.group)
 
+    def Allgather_fields(self, field, fields):
+        """fields[r] <- the ``field`` of rank r, for every rank: ONE collective moving each field once over NVLink (the
+        node-parallel sweepers gather the right-hand sides of all collocation nodes with it)."""
+        send = self._storage(field)
+        recv = [self._storage(f) for f in fields]
+        if self._host_staged and send.is_cuda:
+            hs = [torch.empty(t.shape, dtype=t.dtype) for t in recv]
+            dist.all_gather(hs, send.cpu(), group=self.group)
+            for t, h in zip(recv, hs):
+                t.copy_(h)
+        else:
+            dist.all_gather(recv, send.contiguous(), group=self.group)
+
     # ---- one Python scalar between neighbours (convergence status ring, check_convergence.py:146-157) ----------
     def send_scalar(self, value, dest):
         t = torch.tensor([float(value)], dtype=torch.float64, device=self.device)

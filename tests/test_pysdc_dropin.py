@@ -49,7 +49,9 @@ def test_shipped_reference_is_unmodified():
 
 @pytest.mark.parametrize("name", ["run_heat3d_gi_minsrns_31", "run_heat3d_gi_lu_31", "run_heat2d_imex_lu_63",
                                   "run_heat1d_imex_ie_step3A", "run_allencahn_gi_lu_64", "run_heat3d_gi_minsrflex_31",
-                                  "run_allencahn_semi_imex_lu_64"])
+                                  "run_allencahn_semi_imex_lu_64", "run_allencahn_semi_v2_imex_lu_64",
+                                  "run_advection2d_gi_lu_gmres10_64", "run_advection3d_gi_minsrns_gmres_32",
+                                  "run_heat2d_imex_lu_gmres_63"])
 def test_reference_controller_drives_plugin_classes(plugin, name):
     from pySDC.core.sweeper import Sweeper
     from pySDC.helpers.stats_helper import get_sorted
@@ -81,7 +83,8 @@ def test_reference_controller_drives_plugin_classes(plugin, name):
     for key in P.work_counters:
         got = [int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")]
         want = g["work_" + key].tolist()
-        assert np.all(np.abs(np.array(got) - np.array(want)) <= np.maximum(np.ceil(0.02 * np.array(want)), 1)), (key, got, want)
+        band = 0.05 if key == "GMRES" else 0.02  # (restarted GMRES: see tests/test_host_cpu.py::test_run)
+        assert np.all(np.abs(np.array(got) - np.array(want)) <= np.maximum(np.ceil(band * np.array(want)), 1)), (key, got, want)
 
 
 def test_reference_pfasst_controller_drives_plugin_classes(plugin):
