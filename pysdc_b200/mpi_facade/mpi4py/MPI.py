@@ -15,6 +15,7 @@ from pysdc_b200.parallel import Request, TorchComm
 # reduction operations / datatypes (opaque tokens)
 LAND, LOR, MAX, MIN, SUM = _ops.LAND, _ops.LOR, _ops.MAX, _ops.MIN, _ops.SUM
 DOUBLE, INT, BOOL = "double", "int", "bool"
+_RED = {MAX: dist.ReduceOp.MAX, MIN: dist.ReduceOp.MIN, SUM: dist.ReduceOp.SUM}
 REQUEST_NULL = None
 UNDEFINED = -32766
 
@@ -146,6 +147,36 @@ class Intracomm:
     def Ibcast(self, buf, root=0):
         self.Bcast(buf, root=root)
         return Request()
+
+    # ---- buffer reductions (the node-parallel sweepers: generic_implicit_MPI.py:176-196,241-267) -------------------
+    def _reduce_buffer(self, sendbuf, recvbuf, op, root):
+        """root=None: all ranks receive.  Device fields are reduced where they live (NCCL); numpy buffers as tensors."""
+        tc = self.tc
+        if hasattr(sendbuf, "_buf") or torch.is_tensor(sendbuf):
+            src = tc._storage(sendbuf)
+            t = src.cpu() if (tc._host_staged and src.is_cuda) else src.clone()
+        else:
+            a = np.ascontiguousarray(_array(sendbuf), dtype=np.float64)
+            t = torch.from_numpy(a.copy().ravel()).to(tc.device)
+        if root is None:
+            dist.all_reduce(t, op=_RED[op], group=tc.group)
+        else:
+            dist.reduce(t, dst=tc._global(root), op=_RED[op], group=tc.group)
+        if recvbuf is None or (root is not None and tc.rank != root):
+            return
+        if hasattr(recvbuf, "_buf") or torch.is_tensor(recvbuf):
+            tc._storage(recvbuf).copy_(t)
+            if hasattr(recvbuf, "_touch"):
+                recvbuf._touch()
+        else:
+            out = _array(recvbuf)
+            out[...] = t.cpu().numpy().reshape(out.shape)
+
+    def Reduce(self, sendbuf, recvbuf, op=SUM, root=0):
+        self._reduce_buffer(sendbuf, recvbuf, op, root)
+
+    def Allreduce(self, sendbuf, recvbuf, op=SUM):
+        self._reduce_buffer(sendbuf, recvbuf, op, None)
 
 
 Comm = Intracomm

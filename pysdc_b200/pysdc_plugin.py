@@ -21,4 +21,5 @@ globals().update({k: v for k, v in _problems._bind(_PySDCProblem).items()})
 globals().update({k: v for k, v in _sweepers._bind(_PySDCSweeper).items()})
 
 __all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "allencahn_semiimplicit",
-           "allencahn_semiimplicit_v2", "generic_implicit", "imex_1st_order", "mesh_to_mesh"]
+           "allencahn_semiimplicit_v2", "generic_implicit", "imex_1st_order", "generic_implicit_MPI", "imex_1st_order_MPI",
+           "mesh_to_mesh"]

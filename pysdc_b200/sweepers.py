@@ -328,10 +328,212 @@ class Imex1stOrderMixin(_SweepCommon):
         self.QE = self.get_Qdelta_explicit(qd_type=self.params.QE)
 
 
+class NodeParallelMixin:
+    """``SweeperMPI`` (sweeper_classes/generic_implicit_MPI.py:8-164): parallel across the method, one collocation node
+    per rank / GPU, for diagonal QDelta.  Placed in front of the sweeper mix-in like the reference's multiple inheritance
+    (``class generic_implicit_MPI(SweeperMPI, generic_implicit)``, :167).
+
+    The reference moves every node's right-hand side M times per quadrature (M ``comm.Reduce`` of full vectors,
+    :176-196 — and twice per sweep, for ``update_nodes`` and for the residual).  Here the right-hand side of the own
+    node is ALL-GATHERED once after it changed (one NCCL collective over NVLink, each field crosses once), after which
+    the quadrature of the own node, the residual and the end-point update are local launches of the fused collocation
+    kernels on the gathered fields.  The sums run over the nodes in the serial sweeper's order j = 1..M (an MPI reduction
+    has no defined order), so a node-parallel run reproduces the serial diagonal-QDelta sweep bit for bit.  Like in the
+    reference only ``L.u[rank+1]`` / ``L.f[rank+1]`` (and index 0) exist on a rank."""
+
+    def __init__(self, params, level):
+        if "comm" not in params:  # generic_implicit_MPI.py:35-37 (MPI.COMM_WORLD)
+            from .parallel import TorchComm
+
+            params["comm"] = TorchComm()
+        super().__init__(params, level)
+        if self.params.comm.size != self.coll.num_nodes:
+            raise NotImplementedError(
+                f"The communicator in the {type(self).__name__} sweeper needs to have one rank for each node as of now! "
+                f"That means we need {self.coll.num_nodes} nodes, but got {self.params.comm.size} processes.")
+        self._fall, self._fall_key = None, None
+
+    @property
+    def comm(self):
+        return self.params.comm
+
+    @property
+    def rank(self):
+        return self.comm.rank
+
+    @property
+    def _tc(self):
+        return getattr(self.comm, "tc", self.comm)  # the mpi4py facade wraps a TorchComm
+
+    # ---- the gathered right-hand sides ------------------------------------------------------------------------------
+    def _all_f(self, L):
+        """f of every node, current: one all-gather whenever the own node's f changed since the last one (every rank
+        runs the same program, so the decision is the same on all of them)."""
+        own = L.f[self.rank + 1]
+        key = self._field_key(own)
+        if self._fall is None:
+            self._fall = [L.prob.dtype_f(L.prob.init) for _ in range(self.coll.num_nodes)]
+        if self._fall_key != key:
+            self._tc.Allgather_fields(own, self._fall)
+            self._fall_key = key
+        return self._fall
+
+    def _gathered_inputs(self, L):
+        ins = []
+        for f in self._all_f(L):
+            ins += [f.impl.flat, f.expl.flat] if self.imex else [f.flat]
+        return ins
+
+    # ---- predictor (generic_implicit_MPI.py:124-157) ----------------------------------------------------------------
+    def predict(self):
+        L = self.level
+        P = L.prob
+        m = self.rank
+        guess = self.params.initial_guess
+        t_m = L.time + L.dt * self.coll.nodes[m]
+        if guess == "spread":
+            L.u[m + 1] = P.dtype_u(L.u[0])
+            if hasattr(P, "eval_f_batch"):
+                L.f[0], L.f[m + 1] = P.dtype_f(P.init), P.dtype_f(P.init)
+                P.eval_f_batch([L.u[0], L.u[m + 1]], [L.time, t_m], [L.f[0], L.f[m + 1]])
+            else:
+                L.f[0] = P.eval_f(L.u[0], L.time)
+                L.f[m + 1] = P.eval_f(L.u[m + 1], t_m)
+        elif guess == "copy":
+            L.f[0] = P.eval_f(L.u[0], L.time)
+            L.u[m + 1] = P.dtype_u(L.u[0])
+            L.f[m + 1] = P.dtype_f(L.f[0])
+        elif guess == "zero":
+            L.f[0] = P.eval_f(L.u[0], L.time)
+            L.u[m + 1] = P.dtype_u(init=P.init, val=0.0)
+            L.f[m + 1] = P.dtype_f(init=P.init, val=0.0)
+        else:
+            raise ParameterError(f"initial_guess option {guess} not implemented")
+        L.status.unlocked = True
+        L.status.updated = True
+        self._res_cache, self._fall_key = None, None
+
+    # ---- integrate (generic_implicit_MPI.py:176-196, imex_1st_order_MPI.py:14-38) -----------------------------------
+    def integrate(self, last_only=False):
+        """The own node's row of ``dt Q F`` (ONE field, not a list); with ``last_only`` only the last rank gets it."""
+        L = self.level
+        me = L.prob.dtype_u(L.prob.init, val=0.0)
+        ins = self._gathered_inputs(L)
+        if not last_only or self.rank == self.coll.num_nodes - 1:
+            get_backend().colloc_sweep(ins, self._ncomp, [me.flat],
+                                       Wq=L.dt * self.coll.Qmat[self.rank + 1: self.rank + 2, 1:])
+        return me
+
+    # ---- one sweep (generic_implicit_MPI.py:198-239, imex_1st_order_MPI.py:40-88) -----------------------------------
+    def update_nodes(self):
+        L = self.level
+        P = L.prob
+        assert L.status.unlocked
+        r = self.rank
+        dt = L.dt
+        alpha = dt * self.QI[r + 1, r + 1]
+        t_r = L.time + dt * self.coll.nodes[r]
+        # rhs = (dt Q F)[r] - dt*QDelta[r+1, r+1] f[r+1] + u[0] + tau[r], one fused pass over the gathered fields
+        M = self.coll.num_nodes
+        Wi = np.zeros((1, M))
+        Wi[0, r] = -self.QI[r + 1, r + 1]
+        if self.imex:
+            qd = dict(Wi=Wi, We=np.zeros((1, M)), dt2=dt)  # QE = PIC (imex_1st_order_MPI.py:9-12)
+        else:
+            qd = dict(Wi=dt * Wi)
+        rhs = self._scratch(L, 1)[0]
+        tau = None if L.tau[r] is None else [L.tau[r].flat]
+        get_backend().colloc_sweep(self._gathered_inputs(L), self._ncomp, [rhs.flat], Wq=dt * self.coll.Qmat[r + 1: r + 2, 1:],
+                                   base=L.u[0].flat, adds=tau, **qd)
+        self._own(L.u, r + 1)
+        self._own(L.f, r + 1)
+        if hasattr(P, "solve_system_batch") and hasattr(P, "eval_f_batch"):
+            P.solve_system_batch([rhs], [alpha], [L.u[r + 1]], [t_r])
+            P.eval_f_batch([L.u[r + 1]], [t_r], [L.f[r + 1]])
+        else:
+            L.u[r + 1] = P.solve_system(rhs, alpha, L.u[r + 1], t_r)
+            L.f[r + 1] = P.eval_f(L.u[r + 1], t_r)
+        L.status.updated = True
+        self._res_cache, self._fall_key = None, None
+        return None
+
+    # ---- residual (generic_implicit_MPI.py:80-122) ------------------------------------------------------------------
+    def compute_residual(self, stage=None):
+        L = self.level
+        if stage in self.params.skip_residual_computation:
+            L.status.residual = 0.0 if L.status.residual is None else L.status.residual
+            return None
+        rtype = L.params.residual_type
+        if rtype not in ("full_abs", "last_abs", "full_rel", "last_rel"):
+            raise NotImplementedError(f'residual type "{rtype}" not implemented!')
+        r, M = self.rank, self.coll.num_nodes
+        key = (L.dt, rtype, self._field_key(L.u[0]), self._field_key(L.u[r + 1]), self._field_key(L.f[r + 1]),
+               self._field_key(L.tau[r]))
+        cache = getattr(self, "_res_cache", None)
+        if not L.status.updated and cache is not None and cache[0] == key:
+            L.status.residual = cache[1]  # second request of an iteration (controller_nonMPI.py:493 after :573)
+            return None
+        be = get_backend()
+        if "_resnorm" not in self.__dict__:
+            self._resnorm = be.zeros(M + 1)
+        norms = self._resnorm
+        norms.zero_()
+        ins = self._gathered_inputs(L)
+        if rtype.startswith("full") or r == M - 1:
+            be.colloc_residual(L.dt * self.coll.Qmat[r + 1: r + 2, 1:], ins, self._ncomp, L.u[0].flat, [L.u[r + 1].flat],
+                               None if L.tau[r] is None else [L.tau[r].flat], None, norms[r: r + 1])
+        if rtype.endswith("_rel"):
+            be.maxabs_async(L.u[0].vol, norms[M: M + 1])
+        from .comm import MAX
+
+        self._tc.allreduce_device(norms, MAX)  # every rank gets all M node norms: one collective, then one read
+        host = norms.cpu().tolist()
+        res = max(host[:M]) if rtype.startswith("full") else host[M - 1]
+        L.status.residual = res / host[M] if rtype.endswith("_rel") else res
+        L.status.updated = False
+        self._res_cache = (key, L.status.residual)
+        return None
+
+    # ---- end point (generic_implicit_MPI.py:53-78,241-267, imex_1st_order_MPI.py:90-124) ----------------------------
+    def compute_end_point(self):
+        L = self.level
+        P = L.prob
+        root = self.comm.Get_size() - 1
+        if self.coll.right_is_node and not self.params.do_coll_update:
+            L.uend = P.dtype_u(L.u[-1]) if self.rank == root else P.dtype_u(L.u[0])
+            self._tc.Bcast(L.uend, root=root)
+        else:
+            # uend = sum_m dt*w_m f[m+1]; uend += u[0]; uend += tau[-1] (broadcast from the last rank)
+            L.uend = P.dtype_u(P.init)
+            tau = None
+            if L.tau[self.rank] is not None:
+                self.communicate_tau_correction_for_full_interval()
+                tau = [L.tau[-1].flat]
+            get_backend().colloc_sweep(self._gathered_inputs(L), self._ncomp, [L.uend.flat],
+                                       Wq=(L.dt * self.coll.weights)[None, :], base=L.u[0].flat, adds=tau)
+        return None
+
+    def communicate_tau_correction_for_full_interval(self):
+        L = self.level
+        if self.rank < self.comm.size - 1:
+            L.tau[-1] = L.prob.u_init
+        self._tc.Bcast(L.tau[-1], root=self.comm.size - 1)
+
+
+class Imex1stOrderNodeParallelMixin(NodeParallelMixin):
+    def __init__(self, params, level):
+        super().__init__(params, level)
+        assert self.params.QE == "PIC", (f"Only Picard is implemented for explicit preconditioner so far in "
+                                         f"{type(self).__name__}! You chose \"{self.params.QE}\"")
+
+
 def _bind(base):
     ns = {}
     for name, mixin in (("generic_implicit", GenericImplicitMixin), ("imex_1st_order", Imex1stOrderMixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
+    for name, par, mixin in (("generic_implicit_MPI", NodeParallelMixin, GenericImplicitMixin),
+                             ("imex_1st_order_MPI", Imex1stOrderNodeParallelMixin, Imex1stOrderMixin)):
+        ns[name] = type(name, (par, mixin, base), {"__doc__": NodeParallelMixin.__doc__, "__module__": __name__})
     return ns
 
 

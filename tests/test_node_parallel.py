@@ -1,0 +1,155 @@
+"""Node-parallel ("parallel across the method") sweepers: one collocation node per rank / GPU.
+
+Expected values are fixtures of the reference's OWN ``generic_implicit_MPI`` / ``imex_1st_order_MPI`` sweepers
+(sweeper_classes/generic_implicit_MPI.py, imex_1st_order_MPI.py), unmodified, run with one process per node by
+oracle/make_golden_node_parallel.py (which also checks them against the reference's serial sweepers).
+
+Three ways through the code, each as a ``numpy`` variant (gloo + the numpy test double, CPU suite) and a ``cuda`` variant
+(``-m gpu``: the real kernels; NCCL when the box has a GPU per node, otherwise the ranks share the device and the
+collectives are staged through gloo):
+
+* ``own``        pysdc_b200's sweepers + problem classes under pysdc_b200's stand-alone controller;
+* ``plugin``     the same classes bound to pySDC's bases under the reference's own ``controller_nonMPI``;
+* ``reference``  the reference's unmodified ``*_MPI`` sweepers (M ``comm.Reduce`` of full fields per quadrature) on the
+                 mpi4py facade, driving the plug-in PROBLEM classes — device fields through ``Reduce / Allreduce / Bcast``.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, free_port, load_golden, reference_paths
+
+REF_PATHS = reference_paths()
+CASES = ["nodepar_heat3d_gi_minsrns_31", "nodepar_heat2d_gi_minsrs_collupdate_63", "nodepar_heat2d_imex_minsrs_pic_63"]
+
+
+def _worker(rank, world, port, name, out_dir, kind, mode, ref_paths):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    if mode != "own":
+        for p in reversed(ref_paths):
+            sys.path.insert(0, p)
+        import pysdc_b200.mpi_facade
+
+        sys.path.insert(0, pysdc_b200.mpi_facade.PATH)
+    transport = "gloo"
+    if kind == "cuda":
+        import torch
+
+        transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(transport, rank=rank, world_size=world)
+    try:
+        from pysdc_b200 import backend
+
+        if kind == "cuda":
+            backend.set_backend(backend.CudaBackend())
+        else:
+            from fake_backend import NumpyBackend
+
+            backend.set_backend(NumpyBackend())
+        spec, _ = load_golden(name)
+        pp = dict(spec["problem_params"])
+        pp["nvars"], pp["freq"] = tuple(pp["nvars"]), tuple(pp["freq"])
+        sp = dict(spec["sweeper_params"])
+        if mode == "own":
+            from pysdc_b200 import problems, sweepers
+            from pysdc_b200.controller import LogWork, controller_nonMPI
+            from pysdc_b200.parallel import TorchComm
+            from pysdc_b200.stats import get_sorted
+
+            prob, sweep, sp["comm"] = getattr(problems, spec["problem"]), getattr(sweepers, spec["sweeper"] + "_MPI"), TorchComm()
+        else:
+            from mpi4py import MPI  # the facade
+            from pySDC.helpers.stats_helper import get_sorted
+            from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+            from pySDC.implementations.hooks.log_work import LogWork
+
+            from pysdc_b200 import pysdc_plugin as plugin
+
+            prob, sp["comm"] = getattr(plugin, spec["problem"]), MPI.COMM_WORLD
+            if mode == "plugin":
+                sweep = getattr(plugin, spec["sweeper"] + "_MPI")
+            else:
+                import importlib
+
+                mod = importlib.import_module(f"pySDC.implementations.sweeper_classes.{spec['sweeper']}_MPI")
+                sweep = getattr(mod, spec["sweeper"] + "_MPI")
+        d = dict(problem_class=prob, problem_params=pp, sweeper_class=sweep, sweeper_params=sp,
+                 level_params=dict(spec["level_params"]), step_params=dict(spec["step_params"]))
+        c = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40, "hook_class": [LogWork]}, description=d)
+        P = c.MS[0].levels[0].prob
+        if spec["u0"] == "exact":
+            u0 = P.u_exact(spec["t0"])
+        else:
+            u0 = P.u_init
+            u0[:] = np.random.default_rng(spec["seed"]).standard_normal(P.nvars)
+        launches0 = backend.get_backend().launches
+        uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+        its = get_sorted(stats, type="niter", sortby="time")
+        res = [[float(v) for _, v in get_sorted(stats, time=t, type="residual_post_iteration", sortby="iter")] for t, _ in its]
+        out = dict(niter=[int(v) for _, v in its], residuals=res,
+                   work_CG=[int(v) for _, v in get_sorted(stats, type="work_CG", sortby="time")],
+                   launches=backend.get_backend().launches - launches0)
+        with open(os.path.join(out_dir, f"out_{rank}.json"), "w") as f:
+            json.dump(out, f)
+        np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.get())
+        if mode == "own" and rank == 0 and not sp.get("do_coll_update", False):
+            # the gathered quadrature sums over the nodes in the serial sweeper's order: same bits as the serial
+            # (node-batched) diagonal-QDelta sweep on one device
+            sp.pop("comm")
+            d.update(sweeper_class=getattr(sweepers, spec["sweeper"]), sweeper_params=sp)
+            c = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40}, description=d)
+            serial, _ = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+            assert np.array_equal(serial.get(), uend.get())
+    finally:
+        dist.destroy_process_group()
+
+
+def _check(tmp_path, name, kind, mode):
+    spec, g = load_golden(name)
+    world = spec["sweeper_params"]["num_nodes"]
+    mp.spawn(_worker, args=(world, free_port(), name, str(tmp_path), kind, mode, REF_PATHS), nprocs=world, join=True)
+    outs = [json.load(open(os.path.join(tmp_path, f"out_{r}.json"))) for r in range(world)]
+    uends = [np.load(os.path.join(tmp_path, f"uend_{r}.npy")) for r in range(world)]
+    for r in range(world):
+        assert outs[r]["niter"] == g["niter"].tolist(), (r, outs[r]["niter"])
+        assert np.array_equal(uends[r], uends[0])  # the broadcast / the all-gathered quadrature: same bits on every rank
+        assert np.max(np.abs(uends[r] - g["uend"])) / np.max(np.abs(g["uend"])) < 1e-10
+        assert outs[r]["launches"] > 0
+        for got, want in zip(outs[r]["residuals"], g["residuals"]):
+            want = want[~np.isnan(want)]
+            assert len(got) == len(want)
+            # 1e-6 relative above the solver noise floor, like the serial runs (parity_cases.check_run)
+            np.testing.assert_allclose(got, want, rtol=1e-6, atol=2e-11 * max(1.0, float(g["uend_maxabs"])))
+        # every rank solves its own node: CG work per rank and step as the reference's ranks did it (the stopping test
+        # sits on a rounding-sensitive threshold: +-2 %, or one iteration on every other solve of the step)
+        want = g["work_CG_per_rank"][r]
+        slack = np.maximum(np.ceil(0.02 * want), g["niter"] // 2)
+        assert np.all(np.abs(np.array(outs[r]["work_CG"]) - want) <= slack), (r, outs[r]["work_CG"], want)
+
+
+@pytest.mark.parametrize("kind", ["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", CASES)
+def test_node_parallel_sweepers_standalone(tmp_path, name, kind):
+    _check(tmp_path, name, kind, "own")
+
+
+@pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+@pytest.mark.parametrize("kind", ["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", CASES)
+def test_node_parallel_sweepers_under_the_reference_controller(tmp_path, name, kind):
+    _check(tmp_path, name, kind, "plugin")
+
+
+@pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+@pytest.mark.parametrize("kind", ["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("name", CASES)
+def test_reference_node_parallel_sweepers_on_the_facade(tmp_path, name, kind):
+    _check(tmp_path, name, kind, "reference")
