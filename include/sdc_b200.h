@@ -233,6 +233,17 @@ int sdcb200_allencahn_newton_solve(int n, int B, int variant, const double* fact
                                    int newton_maxiter, double lin_tol, int lin_maxiter, double inexact_ratio,
                                    void* work, size_t work_bytes, int* counters_dev, void* stream);
 
+/* Point-wise Newton solve of the reaction part,  u_b - factor_b (1/eps^2) u_b (1 - u_b^nu) = rhs_b  on `count` grid
+ * points for B systems in one persistent launch: allencahn_multiimplicit.solve_system_2 (AllenCahn_2D_FD.py:594-651).
+ * Global loop as in the reference (all points take the same number of updates, decided by max|g| < newton_tol over the
+ * grid, at most newton_maxiter); its diagonal Jacobian system is solved exactly (the limit of the reference's CG).
+ * u[b]: in = initial guess, out = solution.  counters_dev[0] += Newton updates (summed over the systems).
+ * work: sdcb200_reaction_workspace_bytes() bytes, 256-byte aligned.                                                  */
+size_t sdcb200_reaction_workspace_bytes(void);
+int sdcb200_allencahn_reaction_newton(long long count, int B, const double* factor_host, double inv_eps2, int nu_exp,
+                                      const double* const* rhs, double* const* u, double newton_tol, int newton_maxiter,
+                                      void* work, size_t work_bytes, int* counters_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,17 +30,20 @@ from pySDC.helpers.stats_helper import get_sorted  # noqa: E402
 from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI  # noqa: E402
 from pySDC.implementations.hooks.log_work import LogWork  # noqa: E402
 from pySDC.implementations.problem_classes.AllenCahn_2D_FD import (  # noqa: E402
-    allencahn_fullyimplicit, allencahn_semiimplicit, allencahn_semiimplicit_v2)
+    allencahn_fullyimplicit, allencahn_multiimplicit, allencahn_multiimplicit_v2, allencahn_semiimplicit,
+    allencahn_semiimplicit_v2)
 from pySDC.implementations.problem_classes.AdvectionEquation_ND_FD import advectionNd  # noqa: E402
 from pySDC.implementations.problem_classes.HeatEquation_ND_FD import heatNd_forced, heatNd_unforced  # noqa: E402
 from pySDC.implementations.sweeper_classes.generic_implicit import generic_implicit  # noqa: E402
 from pySDC.implementations.sweeper_classes.imex_1st_order import imex_1st_order  # noqa: E402
+from pySDC.implementations.sweeper_classes.multi_implicit import multi_implicit  # noqa: E402
 from pySDC.implementations.transfer_classes.TransferMesh import mesh_to_mesh  # noqa: E402
 
 PROBLEMS = {"heatNd_unforced": heatNd_unforced, "heatNd_forced": heatNd_forced, "advectionNd": advectionNd,
             "allencahn_fullyimplicit": allencahn_fullyimplicit, "allencahn_semiimplicit": allencahn_semiimplicit,
-            "allencahn_semiimplicit_v2": allencahn_semiimplicit_v2}
-SWEEPERS = {"generic_implicit": generic_implicit, "imex_1st_order": imex_1st_order}
+            "allencahn_semiimplicit_v2": allencahn_semiimplicit_v2, "allencahn_multiimplicit": allencahn_multiimplicit,
+            "allencahn_multiimplicit_v2": allencahn_multiimplicit_v2}
+SWEEPERS = {"generic_implicit": generic_implicit, "imex_1st_order": imex_1st_order, "multi_implicit": multi_implicit}
 
 
 def _jsonable(d):
@@ -169,6 +172,36 @@ def allencahn_semiimplicit_v2_fixtures():
     run_case("run_allencahn_semi_v2_imex_lu_64", spec)
 
 
+def allencahn_multiimplicit_fixtures():
+    """allencahn_multiimplicit / _v2 with the multi_implicit sweeper (AllenCahn_2D_FD.py:487-776,
+    sweeper_classes/multi_implicit.py): operator vectors of both solves and the TOMS runs
+    (projects/TOMS/AllenCahn_contracting_circle.py:36-62,114-124) at two sizes."""
+    rng = np.random.default_rng(4043)
+    pp = dict(nvars=(32, 32), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9, lin_tol=1e-10, lin_maxiter=100, radius=0.25)
+    for name, cls in (("allencahn_multiimplicit", allencahn_multiimplicit), ("allencahn_multiimplicit_v2", allencahn_multiimplicit_v2)):
+        P = cls(**pp)
+        u = P.u_exact(0.0)
+        u[:] = u + 0.01 * rng.standard_normal(u.shape)
+        rhs = P.dtype_u(u)
+        rhs[:] = u + 0.05 * rng.standard_normal(u.shape)
+        f = P.eval_f(u, 0.0)
+        sol1 = P.solve_system_1(rhs, 1e-3, u, 0.0)
+        n1, l1 = int(P.newton_itercount), int(P.lin_itercount)
+        sol2 = P.solve_system_2(rhs, 1e-3, u, 0.0)
+        save("op_" + name, dict(problem=name, problem_params=_jsonable(pp), t=0.0, factor=1e-3), u=np.asarray(u),
+             rhs=np.asarray(rhs), f=np.asarray(f), sol1=np.asarray(sol1), sol2=np.asarray(sol2),
+             newton_after_1=np.array(n1), linear_after_1=np.array(l1), newton_itercount=np.array(int(P.newton_itercount)),
+             lin_itercount=np.array(int(P.lin_itercount)))
+        for n in (64, 128):
+            spec = dict(problem=name, sweeper="multi_implicit",
+                        problem_params=dict(nvars=[n, n], nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9, lin_tol=1e-10,
+                                            lin_maxiter=100, radius=0.25),
+                        sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", Q1="LU", Q2="LU", initial_guess="zero"),
+                        level_params=dict(dt=1e-3, restol=1e-8), step_params=dict(maxiter=50), t0=0.0, Tend=2e-3, u0="exact")
+            tag = "multi" if name.endswith("implicit") else "multi_v2"
+            run_case(f"run_allencahn_{tag}_lu_{n}", spec)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # full runs through the reference controller
 # ----------------------------------------------------------------------------------------------------------------
@@ -192,13 +225,16 @@ def run_case(name, spec, store_uend=True):
     for key in P.work_counters:
         arrays["work_" + key] = np.array([int(v) for _, v in get_sorted(stats, type="work_" + key, sortby="time")])
     # (allencahn_semiimplicit_v2 inherits a u_exact(t > 0) that cannot digest its own imex right-hand side)
-    if spec["u0"] == "exact" and spec["problem"] not in ("allencahn_fullyimplicit", "allencahn_semiimplicit_v2"):
+    if spec["u0"] == "exact" and spec["problem"] not in ("allencahn_fullyimplicit", "allencahn_semiimplicit_v2",
+                                                         "allencahn_multiimplicit", "allencahn_multiimplicit_v2"):
         arrays["err_vs_exact"] = np.array(float(abs(P.u_exact(spec["Tend"]) - uend)))
     if store_uend:
         arrays["uend"] = np.asarray(uend)
     if hasattr(P, "newton_itercount"):
         arrays["newton_itercount"] = np.array(int(P.newton_itercount))
         arrays["newton_ncalls"] = np.array(int(P.newton_ncalls))
+        arrays["lin_itercount"] = np.array(int(P.lin_itercount))
+        arrays["lin_ncalls"] = np.array(int(P.lin_ncalls))
     save(name, spec, **arrays)
     return arrays
 
@@ -566,7 +602,7 @@ def pfasst_config5():
     print("  PFASST config 5", niter, "wall", wall)
 
 
-FAMILIES = {"gmres": gmres_fixtures, "allencahn_semi_v2": allencahn_semiimplicit_v2_fixtures, "allencahn_semi": allencahn_semiimplicit_fixtures, "runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "transfer": transfer_vectors,
+FAMILIES = {"gmres": gmres_fixtures, "allencahn_multi": allencahn_multiimplicit_fixtures, "allencahn_semi_v2": allencahn_semiimplicit_v2_fixtures, "allencahn_semi": allencahn_semiimplicit_fixtures, "runs": full_runs, "sweeps": sweep_dumps, "ops": operator_vectors, "transfer": transfer_vectors,
             "pfasst": pfasst_runs,
             "pfasst_config5": pfasst_config5}
 

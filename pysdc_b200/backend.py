@@ -66,6 +66,9 @@ def _declare(lib):
         "sdcb200_newton_workspace_bytes": (c_sz, [c_int, c_int]),
         "sdcb200_allencahn_newton_solve": (c_int, [c_int, c_int, c_int, PD, c_d, c_d, c_d, c_int, PP, PP, c_d, c_int, c_d,
                                                    c_int, c_d, _c_dp, c_sz, _c_dp, _c_dp]),
+        "sdcb200_reaction_workspace_bytes": (c_sz, []),
+        "sdcb200_allencahn_reaction_newton": (c_int, [c_ll, c_int, PD, c_d, c_int, PP, PP, c_d, c_int, _c_dp, c_sz, _c_dp,
+                                                      _c_dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the .so does not export what include/sdc_b200.h declares
@@ -326,6 +329,19 @@ class CudaBackend:
             lay.n, len(us), int(variant), _dbl_array(factors), a_diag, a_off, inv_eps2, int(nu_exp), _ptr_array(rhs), _ptr_array(us),
             float(newton_tol), int(newton_maxiter), float(lin_tol), int(lin_maxiter),
             float(inexact_ratio or 0.0), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(), self._stream()))
+
+    def reaction_workspace(self):
+        nbytes = self.lib.sdcb200_reaction_workspace_bytes()
+        return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=self.device)
+
+    def allencahn_reaction_newton(self, factors, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter, work, counters_dev):
+        """Point-wise Newton on the reaction part for the len(us) systems in ONE persistent launch, in place on us[b]
+        (``rhs`` / ``us``: flat views of whole fields)."""
+        self.launches += 1
+        self._check(self.lib.sdcb200_allencahn_reaction_newton(
+            us[0].numel(), len(us), _dbl_array(factors), float(inv_eps2), int(nu_exp), _ptr_array(rhs), _ptr_array(us),
+            float(newton_tol), int(newton_maxiter), work.data_ptr(), work.numel() * 8, counters_dev.data_ptr(),
+            self._stream()))
 
 
 class SlabWork:

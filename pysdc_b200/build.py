@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsdcb200.so")
-SOURCES = ["colloc.cu", "stencil.cu", "cg.cu", "highorder.cu", "gmres.cu", "direct.cu", "peer.cu", "transfer.cu"]
+SOURCES = ["colloc.cu", "stencil.cu", "cg.cu", "highorder.cu", "gmres.cu", "reaction.cu", "direct.cu", "peer.cu", "transfer.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
 

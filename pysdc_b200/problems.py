@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from .backend import get_backend
-from .datatypes import imex_mesh, mesh
+from .datatypes import comp2_mesh, imex_mesh, mesh
 from .layout import get_layout
 from .errors import ProblemError
 from .fields_io import OutputMixin
@@ -670,14 +670,19 @@ class AllenCahnSemiMixin(AllenCahnMixin):
 
         return imex_1st_order
 
+    _fcomps = ("impl", "expl")
+    _count_rhs = True
+
     def _rhs_total(self, f):
-        return f.impl + f.expl  # AllenCahn_2D_FD.py:364-366
+        return getattr(f, self._fcomps[0]) + getattr(f, self._fcomps[1])  # AllenCahn_2D_FD.py:364-366
 
     def eval_f_batch(self, us, ts, fs):
+        c1, c2 = self._fcomps
         self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
-                                  [u.flat for u in us], [f.impl.flat for f in fs], [f.expl.flat for f in fs])
-        for _ in us:
-            self.work_counters["rhs"]()
+                                  [u.flat for u in us], [getattr(f, c1).flat for f in fs], [getattr(f, c2).flat for f in fs])
+        if self._count_rhs:
+            for _ in us:
+                self.work_counters["rhs"]()
 
     def solve_system_batch(self, rhs, factors, xs, ts=None):
         B = len(xs)
@@ -697,10 +702,12 @@ class AllenCahnSemiMixin(AllenCahnMixin):
         if log is not None:
             ev1.record()
             log.append((ev0, ev1, counters.clone()))
-        total = counters.sum(dtype=torch.int32)
+        self._count_linear(counters.sum(dtype=torch.int32))
+        self.lin_ncalls += B
+
+    def _count_linear(self, total):
         self._counters[1:2] += total  # work_counters['linear'] (AllenCahn_2D_FD.py:327-331)
         self._counters[7:8] += total  # lin_itercount (:348)
-        self.lin_ncalls += B
 
 
 class AllenCahnSemiV2Mixin(AllenCahnMixin):
@@ -717,12 +724,16 @@ class AllenCahnSemiV2Mixin(AllenCahnMixin):
 
         return imex_1st_order
 
+    _fcomps = ("impl", "expl")
+
     def _rhs_total(self, f):
-        return f.impl + f.expl
+        return getattr(f, self._fcomps[0]) + getattr(f, self._fcomps[1])
 
     def eval_f_batch(self, us, ts, fs):  # :402-424 (no work counter there)
+        c1, c2 = self._fcomps
         self._be.allencahn_eval_f(self._lay, self.a_diag, self.a_off, 1.0 / self.eps**2, int(self.nu),
-                                  [u.flat for u in us], [f.impl.flat for f in fs], [f.expl.flat for f in fs], split=2)
+                                  [u.flat for u in us], [getattr(f, c1).flat for f in fs], [getattr(f, c2).flat for f in fs],
+                                  split=2)
 
     def _newton_launch(self, factors, rhs, xs, work, counters):
         n = self.nvars[0] * self.nvars[1]
@@ -735,13 +746,83 @@ class AllenCahnSemiV2Mixin(AllenCahnMixin):
         self._counters[6:7] += counters[0:1]
 
 
+class _TwoSolves:
+    """``solve_system_1`` / ``solve_system_2`` of the multi-implicit problem classes on top of their in-place batch forms."""
+
+    dtype_f = comp2_mesh
+    _fcomps = ("comp1", "comp2")
+
+    @classmethod
+    def get_default_sweeper_class(cls):
+        from .sweepers import multi_implicit
+
+        return multi_implicit
+
+    def solve_system_1(self, rhs, factor, u0, t):
+        me = self.dtype_u(u0)
+        self.solve_system_1_batch([rhs], [factor], [me], [t])
+        return me
+
+    def solve_system_2(self, rhs, factor, u0, t):
+        me = self.dtype_u(u0)
+        self.solve_system_2_batch([rhs], [factor], [me], [t])
+        return me
+
+    def solve_system(self, rhs, factor, u0, t):
+        raise ProblemError(f"{type(self).__name__} splits the right-hand side in two implicit parts: use solve_system_1 / "
+                           "solve_system_2 (multi_implicit sweeper)")
+
+    def solve_system_batch(self, rhs, factors, xs, ts=None):
+        self.solve_system(None, None, None, None)
+
+
+class AllenCahnMultiMixin(_TwoSolves, AllenCahnSemiMixin):
+    """``allencahn_multiimplicit`` (AllenCahn_2D_FD.py:487-651): both parts of the right-hand side implicit, one after
+    the other - ``solve_system_1``: the periodic Laplacian on the TMA-pipelined CG (``lin_tol`` / ``lin_maxiter``, counted
+    in ``lin_itercount`` only, :585-590); ``solve_system_2``: the reaction term by a point-wise Newton iteration with the
+    reference's global stopping rule in one persistent launch (``sdcb200_allencahn_reaction_newton``; counted in
+    ``newton_itercount`` only, :648-649).  ``eval_f`` counts nothing (:510-532)."""
+
+    _count_rhs = False
+
+    def solve_system_1_batch(self, rhs, factors, xs, ts=None):
+        AllenCahnSemiMixin.solve_system_batch(self, rhs, factors, xs, ts)
+
+    def _count_linear(self, total):
+        self._counters[7:8] += total
+
+    def solve_system_2_batch(self, rhs, factors, xs, ts=None):
+        if "react" not in self._work:
+            self._work["react"] = self._be.reaction_workspace()
+        self._be.allencahn_reaction_newton(list(factors), 1.0 / self.eps**2, int(self.nu), [r.vol for r in rhs],
+                                           [x.vol for x in xs], self.newton_tol, self.newton_maxiter, self._work["react"],
+                                           self._counters[6:7])
+        self.newton_ncalls += len(xs)
+
+
+class AllenCahnMultiV2Mixin(_TwoSolves, AllenCahnSemiV2Mixin):
+    """``allencahn_multiimplicit_v2`` (AllenCahn_2D_FD.py:655-776): ``solve_system_1`` is the Newton system of
+    ``allencahn_semiimplicit_v2`` (batched Newton kernel, ``variant = 1``); ``solve_system_2`` is the closed-form
+    ``rhs / (1 - factor / eps^2)`` (:774)."""
+
+    def solve_system_1_batch(self, rhs, factors, xs, ts=None):
+        AllenCahnMixin.solve_system_batch(self, rhs, factors, xs, ts)
+
+    def solve_system_2_batch(self, rhs, factors, xs, ts=None):
+        for r, factor, x in zip(rhs, factors, xs):
+            self._be.axpby(1.0 / (1.0 - factor * 1.0 / self.eps**2), r.vol, 0.0, None, x.vol)
+            x._touch()
+
+
 def _bind(base):
     """Concrete problem classes over a given ``Problem`` base class."""
     ns = {}
     for name, mixin in (("heatNd_unforced", HeatMixin), ("heatNd_forced", HeatForcedMixin),
                         ("advectionNd", AdvectionMixin),
                         ("allencahn_fullyimplicit", AllenCahnMixin), ("allencahn_semiimplicit", AllenCahnSemiMixin),
-                        ("allencahn_semiimplicit_v2", AllenCahnSemiV2Mixin)):
+                        ("allencahn_semiimplicit_v2", AllenCahnSemiV2Mixin),
+                        ("allencahn_multiimplicit", AllenCahnMultiMixin),
+                        ("allencahn_multiimplicit_v2", AllenCahnMultiV2Mixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
     return ns
 

@@ -14,12 +14,12 @@ from pySDC.core.sweeper import Sweeper as _PySDCSweeper
 
 from . import problems as _problems
 from . import sweepers as _sweepers
-from .datatypes import imex_mesh, mesh  # noqa: F401
+from .datatypes import comp2_mesh, imex_mesh, mesh  # noqa: F401
 from .transfer import mesh_to_mesh  # noqa: F401  (space_transfer_class for multi-level runs)
 
 globals().update({k: v for k, v in _problems._bind(_PySDCProblem).items()})
 globals().update({k: v for k, v in _sweepers._bind(_PySDCSweeper).items()})
 
 __all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "allencahn_semiimplicit",
-           "allencahn_semiimplicit_v2", "generic_implicit", "imex_1st_order", "generic_implicit_MPI", "imex_1st_order_MPI",
+           "allencahn_semiimplicit_v2", "allencahn_multiimplicit", "allencahn_multiimplicit_v2", "multi_implicit", "generic_implicit", "imex_1st_order", "generic_implicit_MPI", "imex_1st_order_MPI",
            "mesh_to_mesh"]

@@ -63,6 +63,7 @@ class _SweepCommon:
     """Methods shared by both sweepers; ``self.coll / self.params / self.level / self.QI`` come from the base class."""
 
     imex = False
+    _comps = ("impl", "expl")  # names of the two right-hand-side components when imex
 
     @property
     def _ncomp(self):
@@ -75,7 +76,7 @@ class _SweepCommon:
         for j in range(first, self.coll.num_nodes + 1):
             f = L.f[j]
             if self.imex:
-                ins += [f.impl.flat, f.expl.flat]
+                ins += [getattr(f, self._comps[0]).flat, getattr(f, self._comps[1]).flat]
             else:
                 ins.append(f.flat)
         return ins
@@ -328,6 +329,70 @@ class Imex1stOrderMixin(_SweepCommon):
         self.QE = self.get_Qdelta_explicit(qd_type=self.params.QE)
 
 
+class MultiImplicitMixin(_SweepCommon):
+    """``multi_implicit`` (sweeper_classes/multi_implicit.py:4-160): first-order sweeper for a right-hand side split in two
+    parts ``comp1`` / ``comp2`` that are BOTH treated implicitly, one after the other, with their own QDelta (``Q1``,
+    ``Q2``) and their own solver (``P.solve_system_1`` / ``P.solve_system_2``).  ``integrate``, the residual, the
+    predictor and the end point are the two-component forms of the common sweeper (``f.comp1 + f.comp2``)."""
+
+    imex = True
+    _comps = ("comp1", "comp2")
+
+    def __init__(self, params, level):
+        if "Q1" not in params:
+            params["Q1"] = "IE"
+        if "Q2" not in params:
+            params["Q2"] = "IE"
+        super().__init__(params, level)
+        self.Q1 = self.get_Qdelta_implicit(qd_type=self.params.Q1)
+        self.Q2 = self.get_Qdelta_implicit(qd_type=self.params.Q2)
+
+    def update_nodes(self):
+        """multi_implicit.py:60-132.  Known terms ``u0 + dt (Q F - Q1 F1) + tau`` of all nodes and ``dt Q2 F2`` of all
+        nodes: two fused launches; per node one small launch per implicit part for the terms of the nodes already updated
+        (:108-110,:118-120), in place on the scratch right-hand sides."""
+        L = self.level
+        P = L.prob
+        assert L.status.unlocked
+        be = get_backend()
+        M = self.coll.num_nodes
+        dt = L.dt
+        Q, Q1, Q2 = self.coll.Qmat, self.Q1, self.Q2
+        scratch = self._scratch(L, 2 * M)
+        integral, q2int = scratch[:M], scratch[M: 2 * M]
+        taus = [None if t is None else t.flat for t in L.tau]
+        be.colloc_sweep(self._f_inputs(L), 2, [r.flat for r in integral], Wq=dt * Q[1:, 1:], Wi=-Q1[1:, 1:],
+                        We=np.zeros((M, M)), dt2=dt, base=L.u[0].flat,
+                        adds=taus if any(t is not None for t in taus) else None)
+        be.colloc_sweep([L.f[j].comp2.flat for j in range(1, M + 1)], 1, [q.flat for q in q2int], Wi=dt * Q2[1:, 1:])
+        batched = hasattr(P, "solve_system_1_batch") and hasattr(P, "solve_system_2_batch") and hasattr(P, "eval_f_batch")
+        for m in range(1, M + 1):
+            self._own(L.u, m)
+            self._own(L.f, m)
+        for m in range(M):
+            t = L.time + dt * self.coll.nodes[m]
+            if m > 0 and np.any(Q1[m + 1, 1: m + 1]):
+                be.colloc_sweep([L.f[j].comp1.flat for j in range(1, m + 1)], 1, [integral[m].flat],
+                                Wi=dt * Q1[m + 1: m + 2, 1: m + 1], base=integral[m].flat, base_first=True)
+            if batched:
+                P.solve_system_1_batch([integral[m]], [dt * Q1[m + 1, m + 1]], [L.u[m + 1]], [t])
+            else:
+                L.u[m + 1] = P.solve_system_1(integral[m], dt * Q1[m + 1, m + 1], L.u[m + 1], t)
+            # rhs = u - Q2int[m] + sum_{j<=m} dt*Q2[m+1, j] f[j].comp2   (:116-120), in place on q2int[m]
+            ins = [q2int[m].flat] + [L.f[j].comp2.flat for j in range(1, m + 1)]
+            W = np.concatenate([[-1.0], dt * Q2[m + 1, 1: m + 1]])[None, :]
+            be.colloc_sweep(ins, 1, [q2int[m].flat], Wi=W, base=L.u[m + 1].flat, base_first=True)
+            if batched:
+                P.solve_system_2_batch([q2int[m]], [dt * Q2[m + 1, m + 1]], [L.u[m + 1]], [t])
+                P.eval_f_batch([L.u[m + 1]], [t], [L.f[m + 1]])
+            else:
+                L.u[m + 1] = P.solve_system_2(q2int[m], dt * Q2[m + 1, m + 1], L.u[m + 1], t)
+                L.f[m + 1] = P.eval_f(L.u[m + 1], t)
+        L.status.updated = True
+        self._res_cache = None
+        return None
+
+
 class NodeParallelMixin:
     """``SweeperMPI`` (sweeper_classes/generic_implicit_MPI.py:8-164): parallel across the method, one collocation node
     per rank / GPU, for diagonal QDelta.  Placed in front of the sweeper mix-in like the reference's multiple inheritance
@@ -529,7 +594,8 @@ class Imex1stOrderNodeParallelMixin(NodeParallelMixin):
 
 def _bind(base):
     ns = {}
-    for name, mixin in (("generic_implicit", GenericImplicitMixin), ("imex_1st_order", Imex1stOrderMixin)):
+    for name, mixin in (("generic_implicit", GenericImplicitMixin), ("imex_1st_order", Imex1stOrderMixin),
+                        ("multi_implicit", MultiImplicitMixin)):
         ns[name] = type(name, (mixin, base), {"__doc__": mixin.__doc__, "__module__": __name__})
     for name, par, mixin in (("generic_implicit_MPI", NodeParallelMixin, GenericImplicitMixin),
                              ("imex_1st_order_MPI", Imex1stOrderNodeParallelMixin, Imex1stOrderMixin)):

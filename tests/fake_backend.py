@@ -480,6 +480,23 @@ class NumpyBackend:
                 Mx[-1, 0] += m_off[b]
             self._grid(lay, x)[...] = np.linalg.solve(Mx, self._grid(lay, r))
 
+    def reaction_workspace(self):
+        return torch.zeros(1, dtype=torch.float64)
+
+    def allencahn_reaction_newton(self, factors, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter, work, counters_dev):
+        """sdcb200_allencahn_reaction_newton: global Newton loop, diagonal Jacobian solved exactly."""
+        self.launches += 1
+        for factor, r, u in zip(factors, rhs, us):
+            x, b = _np(u), _np(r)
+            n = 0
+            while n < newton_maxiter:
+                g = x - factor * (inv_eps2 * x * (1.0 - x**nu_exp)) - b
+                if np.max(np.abs(g)) < newton_tol:
+                    break
+                x -= g / (1.0 - factor * (inv_eps2 * (1.0 - (nu_exp + 1) * x**nu_exp)))
+                n += 1
+            counters_dev[0] += n
+
     def allencahn_newton_solve(self, lay, factors, a_diag, a_off, inv_eps2, nu_exp, rhs, us, newton_tol, newton_maxiter,
                                lin_tol, lin_maxiter, inexact_ratio, work, counters_dev, variant=0):
         self.launches += 1

@@ -11,6 +11,7 @@ Tolerances (stated once, used everywhere):
     ||r|| < rtol*||b|| sits on a rounding-sensitive threshold), asserted as a relative band of 2 %.
 """
 import numpy as np
+import pytest
 
 from conftest import load_golden
 
@@ -45,8 +46,11 @@ def classes():
              "advectionNd": problems.advectionNd,
              "allencahn_fullyimplicit": problems.allencahn_fullyimplicit,
              "allencahn_semiimplicit": problems.allencahn_semiimplicit,
-             "allencahn_semiimplicit_v2": problems.allencahn_semiimplicit_v2},
-            {"generic_implicit": sweepers.generic_implicit, "imex_1st_order": sweepers.imex_1st_order})
+             "allencahn_semiimplicit_v2": problems.allencahn_semiimplicit_v2,
+             "allencahn_multiimplicit": problems.allencahn_multiimplicit,
+             "allencahn_multiimplicit_v2": problems.allencahn_multiimplicit_v2},
+            {"generic_implicit": sweepers.generic_implicit, "imex_1st_order": sweepers.imex_1st_order,
+             "multi_implicit": sweepers.multi_implicit})
 
 
 def tuplify(pp):
@@ -87,6 +91,18 @@ def check_operator(name):
     assert type(f) is P.dtype_f
     assert f.shape == g["f"].shape
     assert np.max(np.abs(f.get() - g["f"])) <= stencil_tol(P, np.max(np.abs(g["u"])), g["f"])
+    if "sol1" in g:  # the two solves of the multi-implicit splitting (AllenCahn_2D_FD.py:534-651,699-776)
+        sol1 = P.solve_system_1(rhs, spec["factor"], u, spec["t"])
+        assert type(sol1) is P.dtype_u and relerr(sol1.get(), g["sol1"]) < TOL_SOLVE
+        assert P.newton_itercount == int(g["newton_after_1"]) and close_counts(P.lin_itercount, int(g["linear_after_1"]))
+        sol2 = P.solve_system_2(rhs, spec["factor"], u, spec["t"])
+        assert type(sol2) is P.dtype_u and relerr(sol2.get(), g["sol2"]) < TOL_SOLVE
+        assert P.newton_itercount == int(g["newton_itercount"]) and close_counts(P.lin_itercount, int(g["lin_itercount"]))
+        assert np.array_equal(u.get(), u_before) and np.array_equal(rhs.get(), rhs_before)
+        assert all(c.niter == 0 for c in P.work_counters.values())  # these classes count in the plain ints only
+        with pytest.raises(Exception):
+            P.solve_system(rhs, spec["factor"], u, spec["t"])
+        return
     sol = P.solve_system(rhs, spec["factor"], u, spec["t"])
     assert type(sol) is P.dtype_u
     assert relerr(sol.get(), g["sol"]) < TOL_SOLVE
@@ -259,6 +275,8 @@ def check_run(name, uend_tol=TOL_SOLVE, count_slack=0.02):
             assert close_counts([got[i] for i in keep], [want[i] for i in keep], slack), (key, got, want)
     if "newton_itercount" in g:  # the reference's plain-int totals (AllenCahn_2D_FD.py:202-203,481-482)
         assert P.newton_itercount == int(g["newton_itercount"]) and P.newton_ncalls == int(g["newton_ncalls"])
+    if "lin_itercount" in g:
+        assert close_counts(P.lin_itercount, int(g["lin_itercount"]), count_slack or 0.02) and P.lin_ncalls == int(g["lin_ncalls"])
     return dict(niter=niter, uend=uend, stats=stats)
 
 

@@ -16,6 +16,12 @@ def test_operator_vectors(oracle, name):
     P = oracle.make_problem(spec["problem"], spec["problem_params"])
     f = P.eval_f(g["u"], spec["t"])
     assert _relerr(f, g["f"]) == 0.0  # same scipy matvec, same expression order
+    if "sol1" in g:  # the two solves of the multi-implicit splitting (AllenCahn_2D_FD.py:534-651,699-776)
+        assert _relerr(P.solve_system_1(g["rhs"], spec["factor"], g["u"], spec["t"]), g["sol1"]) == 0.0
+        assert (P.newton_itercount, P.lin_itercount) == (int(g["newton_after_1"]), int(g["linear_after_1"]))
+        assert _relerr(P.solve_system_2(g["rhs"], spec["factor"], g["u"], spec["t"]), g["sol2"]) == 0.0
+        assert (P.newton_itercount, P.lin_itercount) == (int(g["newton_itercount"]), int(g["lin_itercount"]))
+        return
     sol = P.solve_system(g["rhs"], spec["factor"], g["u"], spec["t"])
     assert _relerr(sol, g["sol"]) == 0.0
     if "cg_iters" in g:

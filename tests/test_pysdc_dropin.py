@@ -51,7 +51,8 @@ def test_shipped_reference_is_unmodified():
                                   "run_heat1d_imex_ie_step3A", "run_allencahn_gi_lu_64", "run_heat3d_gi_minsrflex_31",
                                   "run_allencahn_semi_imex_lu_64", "run_allencahn_semi_v2_imex_lu_64",
                                   "run_advection2d_gi_lu_gmres10_64", "run_advection3d_gi_minsrns_gmres_32",
-                                  "run_heat2d_imex_lu_gmres_63"])
+                                  "run_heat2d_imex_lu_gmres_63", "run_allencahn_multi_lu_64",
+                                  "run_allencahn_multi_v2_lu_64"])
 def test_reference_controller_drives_plugin_classes(plugin, name):
     from pySDC.core.sweeper import Sweeper
     from pySDC.helpers.stats_helper import get_sorted
@@ -173,3 +174,37 @@ def test_reference_LogToFile_hook_writes_device_fields(plugin, tmp_path):
     c = controller_nonMPI(num_procs=1, controller_params=dict(logger_level=40, hook_class=[Log]), description=d)
     uend, _ = c.run(u0=umid, t0=0.02, Tend=0.04)
     assert Log.load(-1)["t"] == pytest.approx(0.04) and np.array_equal(Log.load(-1)["u"][0], uend.get())
+
+
+@pytest.mark.parametrize("name", ["run_allencahn_multi_lu_64", "run_allencahn_multi_v2_lu_64", "run_heat2d_imex_lu_63",
+                                  "run_heat3d_gi_lu_31"])
+def test_reference_sweepers_drive_plugin_problem_classes(plugin, name):
+    """Only the PROBLEM class is swapped: the reference's unmodified sweepers (multi_implicit, imex_1st_order,
+    generic_implicit) run their numpy-style arithmetic on the device datatypes (``dt * Q * f.comp1``, ``u - Q2int``,
+    rebinding ``L.u[m+1] = P.solve_system_1(...)``) and call ``solve_system[_1/_2]`` / ``eval_f`` of the plug-in classes."""
+    import importlib
+
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+
+    spec, g = load_golden(name)
+    pp = dict(spec["problem_params"])
+    for k in ("nvars", "freq"):
+        if isinstance(pp.get(k), list):
+            pp[k] = tuple(pp[k])
+    sweeper = getattr(importlib.import_module("pySDC.implementations.sweeper_classes." + spec["sweeper"]), spec["sweeper"])
+    d = dict(problem_class=getattr(plugin, spec["problem"]), problem_params=pp, sweeper_class=sweeper,
+             sweeper_params=dict(spec["sweeper_params"]), level_params=dict(spec["level_params"]),
+             step_params=dict(spec["step_params"]))
+    c = controller_nonMPI(num_procs=1, controller_params={"logger_level": 40}, description=d)
+    P = c.MS[0].levels[0].prob
+    if spec["u0"] == "exact":
+        u0 = P.u_exact(spec["t0"])
+    else:
+        u0 = P.u_init
+        u0[:] = np.random.default_rng(spec["seed"]).standard_normal(P.nvars)
+    uend, stats = c.run(u0=u0, t0=spec["t0"], Tend=spec["Tend"])
+    assert [int(v) for _, v in get_sorted(stats, type="niter", sortby="time")] == g["niter"].tolist()
+    assert np.max(np.abs(uend.get() - g["uend"])) <= 1e-10 * max(float(abs(u0)), float(g["uend_maxabs"]))
+    if "newton_itercount" in g:
+        assert P.newton_itercount == int(g["newton_itercount"]) and P.newton_ncalls == int(g["newton_ncalls"])
