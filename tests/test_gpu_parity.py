@@ -395,6 +395,35 @@ def test_batched_newton_equals_sequential(oracle):
     assert newton_b == want_newton and pc.close_counts(linear_b, want_linear)
 
 
+def test_reaction_newton_against_oracle(oracle):
+    """allencahn_multiimplicit.solve_system_2 (AllenCahn_2D_FD.py:594-651) at a size above the fixtures, single and
+    batched: Newton counts identical to the oracle's global loop (the reference's CG on the diagonal Jacobian vs the exact
+    division differ by lin_tol * |g|), solutions to the solve tolerance, a batched system bit-identical to its own launch;
+    newton_maxiter caps the updates like the reference's while-loop."""
+    from pysdc_b200.problems import allencahn_multiimplicit
+
+    pp = dict(nvars=(512, 512), nu=2, eps=0.04, newton_maxiter=100, newton_tol=1e-9, lin_tol=1e-10, lin_maxiter=100,
+              radius=0.25)
+    P, O = allencahn_multiimplicit(**pp), oracle.AllenCahnMultiFD(**pp)
+    rng = np.random.default_rng(5)
+    u0 = O.u_exact(0.0) + 0.01 * rng.standard_normal(pp["nvars"])
+    factors = [2e-4, 1e-3, 1.2e-3]
+    rhs = [u0 + 0.05 * rng.standard_normal(pp["nvars"]) for _ in factors]
+    xb = [pc.to_mesh(P, u0) for _ in factors]
+    P.solve_system_2_batch([pc.to_mesh(P, r) for r in rhs], factors, xb)
+    batched = P.newton_itercount
+    for fac, r, x in zip(factors, rhs, xb):
+        xs = P.solve_system_2(pc.to_mesh(P, r), fac, pc.to_mesh(P, u0), 0.0)
+        assert np.array_equal(xs.get(), x.get())
+        assert pc.relerr(x.get(), O.solve_system_2(r, fac, u0, 0.0)) < pc.TOL_SOLVE
+    assert batched == O.newton_itercount and P.newton_itercount == 2 * batched and P.newton_ncalls == 6
+    P.newton_maxiter = O.newton_maxiter = 2
+    capped = P.solve_system_2(pc.to_mesh(P, rhs[2]), factors[2], pc.to_mesh(P, u0), 0.0)
+    n0 = O.newton_itercount
+    assert pc.relerr(capped.get(), O.solve_system_2(rhs[2], factors[2], u0, 0.0)) < 1e-9
+    assert P.newton_itercount - 2 * batched == O.newton_itercount - n0 == 2
+
+
 def test_allencahn_diagonal_sweeps_batch_the_node_solves(oracle):
     """allencahn_fullyimplicit with MIN-SR-NS: node-batched Newton through the sweeper vs the oracle's sequential run."""
     spec, _ = load_golden("run_allencahn_gi_lu_64")
