@@ -208,3 +208,36 @@ def test_reference_sweepers_drive_plugin_problem_classes(plugin, name):
     assert np.max(np.abs(uend.get() - g["uend"])) <= 1e-10 * max(float(abs(u0)), float(g["uend_maxabs"]))
     if "newton_itercount" in g:
         assert P.newton_itercount == int(g["newton_itercount"]) and P.newton_ncalls == int(g["newton_ncalls"])
+
+
+def test_reference_adaptivity_runs_on_plugin_classes(plugin):
+    """The reference's step-size controller (convergence_controller_classes/adaptivity.py with EstimateEmbeddedError,
+    StepSizeLimiter-free, restarts through BasicRestarting) on the plug-in classes against the same run on the
+    reference's own classes: same accepted steps, same restarts, same step sizes.  The embedded estimate is a 1e-6-sized
+    difference of two O(1) iterates computed with lintol = 1e-12 solves, so step sizes agree to ~1e-6 relative and the end
+    values to the accuracy that step-size jitter allows (the run's own tolerance is e_tol = 1e-6)."""
+    from pySDC.helpers.stats_helper import get_sorted
+    from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+    from pySDC.implementations.convergence_controller_classes.adaptivity import Adaptivity
+    from pySDC.implementations.problem_classes.HeatEquation_ND_FD import heatNd_forced
+    from pySDC.implementations.sweeper_classes.imex_1st_order import imex_1st_order
+
+    def run(problem_class, sweeper_class):
+        d = dict(problem_class=problem_class,
+                 problem_params=dict(nvars=(63, 63), nu=0.1, freq=(2, 2), bc="dirichlet-zero", solver_type="CG", lintol=1e-12,
+                                     liniter=10000),
+                 sweeper_class=sweeper_class, sweeper_params=dict(num_nodes=3, quad_type="RADAU-RIGHT", QI="LU"),
+                 level_params=dict(dt=0.05, restol=-1), step_params=dict(maxiter=3),
+                 convergence_controllers={Adaptivity: dict(e_tol=1e-6)})
+        c = controller_nonMPI(num_procs=1, controller_params=dict(logger_level=40, mssdc_jac=False), description=d)
+        P = c.MS[0].levels[0].prob
+        uend, stats = c.run(u0=P.u_exact(0.0), t0=0.0, Tend=0.25)
+        dts = [v for _, v in get_sorted(stats, type="dt", recomputed=False)]
+        restarts = sum(v for _, v in get_sorted(stats, type="restart"))
+        return np.asarray(uend.get() if hasattr(uend, "get") else uend), np.array(dts), restarts
+
+    u_ref, dt_ref, restarts_ref = run(heatNd_forced, imex_1st_order)
+    u_dev, dt_dev, restarts_dev = run(plugin.heatNd_forced, plugin.imex_1st_order)
+    assert len(dt_dev) == len(dt_ref) > 5 and restarts_dev == restarts_ref
+    np.testing.assert_allclose(dt_dev, dt_ref, rtol=2e-5)
+    assert np.max(np.abs(u_dev - u_ref)) < 1e-7
