@@ -129,9 +129,10 @@ def _check(tmp_path, name, kind, mode):
             # 1e-6 relative above the solver noise floor, like the serial runs (parity_cases.check_run)
             np.testing.assert_allclose(got, want, rtol=1e-6, atol=2e-11 * max(1.0, float(g["uend_maxabs"])))
         # every rank solves its own node: CG work per rank and step as the reference's ranks did it (the stopping test
-        # sits on a rounding-sensitive threshold: +-2 %, or one iteration on every other solve of the step)
+        # ||r|| < 1e-12 ||b|| of the late sweeps, whose initial guess is almost the solution, is decided by rounding: +-2 %,
+        # or one iteration per solve of the step)
         want = g["work_CG_per_rank"][r]
-        slack = np.maximum(np.ceil(0.02 * want), g["niter"] // 2)
+        slack = np.maximum(np.ceil(0.02 * want), g["niter"])
         assert np.all(np.abs(np.array(outs[r]["work_CG"]) - want) <= slack), (r, outs[r]["work_CG"], want)
 
 
