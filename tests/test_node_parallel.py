@@ -156,3 +156,91 @@ def test_node_parallel_sweepers_under_the_reference_controller(tmp_path, name, k
 @pytest.mark.parametrize("name,kind", _variants(CASES[1:2]))
 def test_reference_node_parallel_sweepers_on_the_facade(tmp_path, name, kind):
     _check(tmp_path, name, kind, "reference")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own test of its node-parallel sweepers (pySDC/tests/test_sweepers/test_MPI_sweeper.py:4-153): one
+# controller step with the MPI sweeper and with the serial one must give the same end point and residual (1e-14), for
+# node counts, node types, residual types, initial guesses, IMEX and a two-level (MLSDC) run that goes through the
+# reference's unmodified base_transfer_MPI (transfer_classes/BaseTransferMPI.py) - here with the plug-in classes
+# ---------------------------------------------------------------------------------------------------------------------
+def _mpi_vs_serial_worker(rank, world, port, kind, cases, ref_paths, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    for p in reversed(ref_paths):
+        sys.path.insert(0, p)
+    import pysdc_b200.mpi_facade
+
+    sys.path.insert(0, pysdc_b200.mpi_facade.PATH)
+    transport = "gloo"
+    if kind == "cuda":
+        import torch
+
+        transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(transport, rank=rank, world_size=world)
+    try:
+        from mpi4py import MPI  # the facade
+        from pySDC.implementations.controller_classes.controller_nonMPI import controller_nonMPI
+        from pySDC.implementations.transfer_classes.BaseTransferMPI import base_transfer_MPI
+
+        from pysdc_b200 import backend
+        from pysdc_b200 import pysdc_plugin as plugin
+
+        if kind == "cuda":
+            backend.set_backend(backend.CudaBackend())
+        else:
+            from fake_backend import NumpyBackend
+
+            backend.set_backend(NumpyBackend())
+
+        def run(use_MPI, quad_type, residual_type, imex, init_guess, ML):
+            name = "imex_1st_order" if imex else "generic_implicit"
+            sp = dict(num_nodes=world, quad_type=quad_type, QI="IEpar", QE="PIC", initial_guess=init_guess)
+            pp = dict(nvars=[(31, 31), (15, 15)] if ML > 1 else (31, 31), bc="dirichlet-zero", freq=(2, 2), nu=0.1,
+                      solver_type="CG", lintol=1e-14, liniter=1000)
+            d = dict(problem_class=plugin.heatNd_forced if imex else plugin.heatNd_unforced, problem_params=pp,
+                     sweeper_class=getattr(plugin, name + ("_MPI" if use_MPI else "")), sweeper_params=sp,
+                     level_params=dict(dt=1e-1, residual_type=residual_type), step_params=dict(maxiter=1))
+            if use_MPI:
+                sp["comm"] = MPI.COMM_WORLD
+            if ML > 1:
+                d.update(space_transfer_class=plugin.mesh_to_mesh)
+                if use_MPI:
+                    d["base_transfer_class"] = base_transfer_MPI
+            c = controller_nonMPI(1, {"logger_level": 40}, d)
+            P = c.MS[0].levels[0].prob
+            u0 = P.u_exact(0) if imex else P.u_exact(0) + 1.0
+            c.run(u0, 0, 1e-1)
+            L = c.MS[0].levels[0]
+            L.sweep.compute_end_point()
+            return L.uend.get(), L.status.residual
+
+        worst = 0.0
+        for case in cases:
+            u_mpi, r_mpi = run(True, *case)
+            u_ser, r_ser = run(False, *case)
+            assert np.allclose(u_mpi, u_ser, atol=1e-13), (case, float(np.max(np.abs(u_mpi - u_ser))))
+            assert np.allclose(r_mpi, r_ser, atol=1e-13), (case, r_mpi, r_ser)
+            worst = max(worst, float(np.max(np.abs(u_mpi - u_ser))))
+        with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
+            f.write(repr(worst))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+@pytest.mark.parametrize("kind,world", [("numpy", 2), ("numpy", 3), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
+def test_mpi_sweeper_equals_serial_sweeper_like_the_reference_test(tmp_path, kind, world):
+    cases = []  # (quad_type, residual_type, imex, initial_guess, ML) as in test_MPI_sweeper.py:156-205
+    for quad_type in ("GAUSS", "RADAU-RIGHT"):
+        for residual_type in ("last_abs", "full_rel"):
+            for imex in (False, True):
+                cases.append((quad_type, residual_type, imex, "spread", 1))
+    cases += [("RADAU-RIGHT", "full_abs", False, "copy", 1), ("RADAU-RIGHT", "full_abs", True, "zero", 1),
+              ("RADAU-RIGHT", "full_abs", False, "spread", 2), ("RADAU-RIGHT", "last_rel", True, "spread", 2)]
+    if kind == "cuda":
+        cases = cases[::3] + cases[-2:]
+    mp.spawn(_mpi_vs_serial_worker, args=(world, free_port(), kind, cases, REF_PATHS, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(tmp_path, f"ok_{r}")) for r in range(world))
