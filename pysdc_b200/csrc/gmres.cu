@@ -54,11 +54,12 @@ struct FdEvalArgs {
     double* f[SDCB200_MAX_NODES + 1];
 };
 
+template <int H>
 __global__ void __launch_bounds__(kThreads) fd_eval_kernel(const __grid_constant__ FdEvalArgs a) {
     for (int b = 0; b < a.B; ++b) {
         const double* u = a.u[b];
         double* f = a.f[b];
-        ho_points(a.g, [&](long long idx, int x, int y, int z) { f[idx] = ho_apply(a.op, a.g, u, x, y, z); });
+        ho_points(a.g, [&](long long idx, int x, int y, int z) { f[idx] = ho_apply<H>(a.op, a.g, u, x, y, z); });
     }
 }
 
@@ -101,6 +102,7 @@ __device__ __forceinline__ double gmres_reduce(const GmresArgs& a, GmresShared& 
     return grid_sum(a.partials, slot, 0, sh.scratch);
 }
 
+template <int H>
 __global__ void __launch_bounds__(kThreads) fd_gmres_kernel(const __grid_constant__ GmresArgs a) {
     __shared__ GmresShared sh;
     const Geom& g = a.g;
@@ -110,15 +112,18 @@ __global__ void __launch_bounds__(kThreads) fd_gmres_kernel(const __grid_constan
     auto Vk = [&](int k) { return a.V + (long long)k * a.field; };
     // M v at a point
     auto Mv = [&](const double* v, long long idx, int x, int y, int z) {
-        return __dsub_rn(v[idx], __dmul_rn(a.factor, ho_apply(a.op, g, v, x, y, z)));
+        return __dsub_rn(v[idx], __dmul_rn(a.factor, ho_apply<H>(a.op, g, v, x, y, z)));
     };
 
     // ||b||
     double acc = 0.0;
-    ho_points(g, [&](long long idx, int, int, int) { acc = fma(a.b[idx], a.b[idx], acc); });
+    flat_quads(g.vol, [&](long long i, bool full) {
+        const Quad b = ldq(a.b, i, full);
+        acc = qdot(b, b, acc);
+    });
     const double bnrm2 = sqrt(gmres_reduce(a, sh, acc, nred));
     if (bnrm2 == 0.0) {  // scipy: return b
-        ho_points(g, [&](long long idx, int, int, int) { a.x[idx] = a.b[idx]; });
+        flat_quads(g.vol, [&](long long i, bool full) { stq(a.x, i, ldq(a.b, i, full), full); });
         return;
     }
     const double atol = a.rtol * bnrm2;  // max(atol = 0, rtol * ||b||)
@@ -145,7 +150,10 @@ __global__ void __launch_bounds__(kThreads) fd_gmres_kernel(const __grid_constan
         {
             double* v0 = Vk(0);
             const double inv = 1.0 / rnorm;
-            ho_points(g, [&](long long idx, int, int, int) { v0[idx] = __dmul_rn(v0[idx], inv); });
+            flat_quads(g.vol, [&](long long i, bool full) {
+                const Quad v = ldq(v0, i, full);
+                stq(v0, i, qmap([&](int e) { return __dmul_rn(qe(v, e), inv); }), full);
+            });
         }
         if (threadIdx.x == 0) {
             for (int i = 0; i <= restart; ++i) sh.S[i] = 0.0;
@@ -173,29 +181,35 @@ __global__ void __launch_bounds__(kThreads) fd_gmres_kernel(const __grid_constan
                 const double* vk = Vk(k);
                 const double* vkm = k > 0 ? Vk(k - 1) : nullptr;
                 acc = 0.0;
-                ho_points(g, [&](long long idx, int, int, int) {
-                    double t = w[idx];
+                flat_quads(g.vol, [&](long long i, bool full) {
+                    Quad t = ldq(w, i, full);
+                    const Quad kq = ldq(vk, i, full);
                     if (vkm != nullptr) {
-                        t = __dsub_rn(t, __dmul_rn(hprev, vkm[idx]));
-                        w[idx] = t;
+                        const Quad m = ldq(vkm, i, full);
+                        t = qmap([&](int e) { return __dsub_rn(qe(t, e), __dmul_rn(hprev, qe(m, e))); });
+                        stq(w, i, t, full);
                     }
-                    acc = fma(vk[idx], t, acc);
+                    acc = qdot(kq, t, acc);
                 });
                 hprev = gmres_reduce(a, sh, acc, nred);
                 if (threadIdx.x == 0) sh.h[col][k] = hprev;
             }
             acc = 0.0;
-            ho_points(g, [&](long long idx, int, int, int) {
-                const double t = __dsub_rn(w[idx], __dmul_rn(hprev, vc[idx]));
-                w[idx] = t;
-                acc = fma(t, t, acc);
+            flat_quads(g.vol, [&](long long i, bool full) {
+                const Quad wq = ldq(w, i, full), c = ldq(vc, i, full);
+                const Quad t = qmap([&](int e) { return __dsub_rn(qe(wq, e), __dmul_rn(hprev, qe(c, e))); });
+                stq(w, i, t, full);
+                acc = qdot(t, t, acc);
             });
             const double h1 = sqrt(gmres_reduce(a, sh, acc, nred));
             if (h1 <= eps * h0) {
                 breakdown = true;  // exact solution indicator
             } else {
                 const double inv = 1.0 / h1;
-                ho_points(g, [&](long long idx, int, int, int) { w[idx] = __dmul_rn(w[idx], inv); });
+                flat_quads(g.vol, [&](long long i, bool full) {
+                    const Quad wq = ldq(w, i, full);
+                    stq(w, i, qmap([&](int e) { return __dmul_rn(qe(wq, e), inv); }), full);
+                });
             }
             if (threadIdx.x == 0) {
                 sh.h[col][col + 1] = breakdown ? 0.0 : h1;
@@ -239,10 +253,16 @@ __global__ void __launch_bounds__(kThreads) fd_gmres_kernel(const __grid_constan
         }
         __syncthreads();
         // x += y @ v[:col+1]
-        ho_points(g, [&](long long idx, int, int, int) {
-            double t = 0.0;
-            for (int k = 0; k <= col; ++k) t = fma(sh.y[k], Vk(k)[idx], t);
-            a.x[idx] = __dadd_rn(a.x[idx], t);
+        flat_quads(g.vol, [&](long long i, bool full) {
+            const Quad xq = ldq(a.x, i, full);
+            Quad t;
+            t.a = t.b = make_double2(0.0, 0.0);
+            for (int k = 0; k <= col; ++k) {
+                const Quad v = ldq(Vk(k), i, full);
+                const double yk = sh.y[k];
+                t = qmap([&](int e) { return fma(yk, qe(v, e), qe(t, e)); });
+            }
+            stq(a.x, i, qmap([&](int e) { return __dadd_rn(qe(xq, e), qe(t, e)); }), full);
         });
         grid_barrier(a.bar);
         // r = b - M x -> V[0]
@@ -298,7 +318,7 @@ int sdcb200_fd_eval_f(int ndim, int n, int bc, int h, const double* coef_host, c
         a.u[b] = u[b];
         a.f[b] = f[b];
     }
-    fd_eval_kernel<<<sm_count() * 8, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    SDC_DISPATCH_H(a.op.h, (fd_eval_kernel<HW><<<sm_count() * 8, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a)));
     SDC_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -338,14 +358,16 @@ int sdcb200_fd_gmres_solve(int ndim, int n, int bc, int h, const double* coef_ho
     a.V = reinterpret_cast<double*>(base + v_off) + sdcb200_guard(ndim, n);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    void* kernel = nullptr;
+    SDC_DISPATCH_H(a.op.h, kernel = (void*)fd_gmres_kernel<HW>);
     int per_sm = 0;
-    SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fd_gmres_kernel, kThreads, 0));
+    SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
     SDC_REQUIRE(per_sm >= 1, "solver kernel does not fit on an SM");
     if (per_sm > 4) per_sm = 4;
     int grid = per_sm * sm_count();
     if (grid > kMaxGrid) grid = kMaxGrid;
     void* params[] = {&a};
-    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)fd_gmres_kernel, dim3(grid), dim3(kThreads), params, 0, s));
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), params, 0, s));
     return 0;
 }
 

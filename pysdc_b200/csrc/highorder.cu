@@ -25,11 +25,12 @@ struct HoEvalArgs {
     const double* profile;
 };
 
+template <int H>
 __global__ void __launch_bounds__(kThreads) ho_eval_kernel(const __grid_constant__ HoEvalArgs a) {
     for (int b = 0; b < a.B; ++b) {
         const double* u = a.u[b];
         ho_points(a.g, [&](long long idx, int x, int y, int z) {
-            a.f[b][idx] = ho_apply(a.op, a.g, u, x, y, z);
+            a.f[b][idx] = ho_apply<H>(a.op, a.g, u, x, y, z);
             if (a.profile != nullptr) a.fexpl[b][idx] = __dmul_rn(a.profile[idx], a.gt[b]);
         });
     }
@@ -49,10 +50,12 @@ struct HoCgArgs {
 };
 
 // M v = v - factor * A v
+template <int H>
 __device__ __forceinline__ double ho_m(const HoCgArgs& a, int b, const double* v, long long idx, int x, int y, int z) {
-    return fma(-a.factor[b], ho_apply(a.op, a.g, v, x, y, z), v[idx]);
+    return fma(-a.factor[b], ho_apply<H>(a.op, a.g, v, x, y, z), v[idx]);
 }
 
+template <int H>
 __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__ HoCgArgs a) {
     __shared__ CgShared sh;
     const Geom& g = a.g;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__
         double bb = 0.0, rr = 0.0;
         ho_points(g, [&](long long idx, int x, int y, int z) {
             const double rhs = S.b[idx];
-            const double r = rhs - ho_m(a, b, S.x, idx, x, y, z);
+            const double r = rhs - ho_m<H>(a, b, S.x, idx, x, y, z);
             S.r[idx] = r;
             bb = fma(rhs, rhs, bb);
             rr = fma(r, r, rr);
@@ -92,7 +95,11 @@ __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__
     }
     __syncthreads();
     for (int b = 0; b < B; ++b)
-        if (sh.bb[b] == 0.0) ho_points(g, [&](long long idx, int, int, int) { a.s[b].x[idx] = 0.0; });
+        if (sh.bb[b] == 0.0) {
+            Quad zero;
+            zero.a = zero.b = make_double2(0.0, 0.0);
+            flat_quads(g.vol, [&](long long i, bool full) { stq(a.s[b].x, i, zero, full); });
+        }
 
     for (int it = 0;; ++it) {
         if (threadIdx.x == 0) {
@@ -112,8 +119,14 @@ __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__
             if (!(act >> b & 1u)) continue;
             const Sys& S = a.s[b];
             const double beta = sh.beta[b];
-            ho_points(g, [&](long long idx, int, int, int) {
-                S.p[idx] = it == 0 ? S.r[idx] : __dadd_rn(__dmul_rn(S.p[idx], beta), S.r[idx]);
+            flat_quads(g.vol, [&](long long i, bool full) {
+                const Quad r = ldq(S.r, i, full);
+                if (it == 0) {
+                    stq(S.p, i, r, full);
+                } else {
+                    const Quad pq = ldq(S.p, i, full);
+                    stq(S.p, i, qmap([&](int e) { return __dadd_rn(__dmul_rn(qe(pq, e), beta), qe(r, e)); }), full);
+                }
             });
         }
         grid_barrier(a.bar);
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__
             const Sys& S = a.s[b];
             double pq = 0.0;
             ho_points(g, [&](long long idx, int x, int y, int z) {
-                const double q = ho_m(a, b, S.p, idx, x, y, z);
+                const double q = ho_m<H>(a, b, S.p, idx, x, y, z);
                 S.q[idx] = q;
                 pq = fma(S.p[idx], q, pq);
             });
@@ -143,11 +156,12 @@ __global__ void __launch_bounds__(kThreads) ho_cg_kernel(const __grid_constant__
             const Sys& S = a.s[b];
             const double alpha = sh.alpha[b];
             double rr = 0.0;
-            ho_points(g, [&](long long idx, int, int, int) {
-                S.x[idx] = __dadd_rn(S.x[idx], __dmul_rn(alpha, S.p[idx]));
-                const double r = __dsub_rn(S.r[idx], __dmul_rn(alpha, S.q[idx]));
-                S.r[idx] = r;
-                rr = fma(r, r, rr);
+            flat_quads(g.vol, [&](long long i, bool full) {
+                const Quad xq = ldq(S.x, i, full), pq = ldq(S.p, i, full), rq = ldq(S.r, i, full), qq = ldq(S.q, i, full);
+                stq(S.x, i, qmap([&](int e) { return __dadd_rn(qe(xq, e), __dmul_rn(alpha, qe(pq, e))); }), full);
+                const Quad r = qmap([&](int e) { return __dsub_rn(qe(rq, e), __dmul_rn(alpha, qe(qq, e))); });
+                stq(S.r, i, r, full);
+                rr = qdot(r, r, rr);
             });
             rr = block_sum(rr, sh.scratch);
             put_partial(a.partials, kSlotB, b, rr);
@@ -213,7 +227,7 @@ int sdcb200_heat_eval_f_ho(int ndim, int n, int bc, int order, const double* cen
             a.gt[b] = gt_host[b];
         }
     }
-    ho_eval_kernel<<<sm_count() * 8, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    SDC_DISPATCH_H(a.op.h, (ho_eval_kernel<HW><<<sm_count() * 8, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a)));
     SDC_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -260,14 +274,16 @@ int sdcb200_heat_cg_solve_ho(int ndim, int n, int bc, int order, const double* c
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     SDC_CUDA_OK(cudaMemsetAsync(a.bar, 0, 256, s));
+    void* kernel = nullptr;
+    SDC_DISPATCH_H(a.op.h, kernel = (void*)ho_cg_kernel<HW>);
     int per_sm = 0;
-    SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ho_cg_kernel, kThreads, 0));
+    SDC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
     SDC_REQUIRE(per_sm >= 1, "solver kernel does not fit on an SM");
     if (per_sm > 4) per_sm = 4;
     int grid = per_sm * sm_count();
     if (grid > kMaxGrid) grid = kMaxGrid;
     void* params[] = {&a};
-    SDC_CUDA_OK(cudaLaunchCooperativeKernel((void*)ho_cg_kernel, dim3(grid), dim3(kThreads), params, 0, s));
+    SDC_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), params, 0, s));
     return 0;
 }
 

@@ -9,7 +9,7 @@
 // (its iterate differs from it by lin_tol * ||g||, which the next Newton step - or the stopping test on g itself -
 // absorbs).  One pass per Newton update: the pass that applies update k also evaluates g at the new point and its
 // max-norm, so an iteration reads u and rhs once, writes u once, and costs one grid barrier.
-#include "cg_common.cuh"
+#include "fdop.cuh"
 
 namespace sdcb200 {
 namespace {
@@ -56,8 +56,6 @@ __global__ void __launch_bounds__(kThreads) reaction_newton_kernel(const __grid_
     __shared__ double scratch[33];
     __shared__ unsigned s_active;
     __shared__ int s_iters[SDCB200_MAX_NODES];
-    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * blockDim.x;
     if (threadIdx.x == 0) {
         s_active = (1u << a.B) - 1u;
         for (int b = 0; b < a.B; ++b) s_iters[b] = 0;
@@ -71,19 +69,20 @@ __global__ void __launch_bounds__(kThreads) reaction_newton_kernel(const __grid_
             if (!(act >> b & 1u)) continue;
             const ReactSys S = a.s[b];
             double gmax = 0.0;
-            for (long long i = gtid; i < a.count2; i += gstride) {
-                double2 u = ld2(S.u + 2 * i);
-                const double2 rhs = ld2(S.rhs + 2 * i);
+            flat_quads(2 * a.count2, [&](long long i, bool full) {  // four points per thread and step, loads first
+                Quad u = ldq(S.u, i, full);
+                const Quad rhs = ldq(S.rhs, i, full);
                 if (!first) {  // Newton update k, then g at the new point
-                    u.x = __dsub_rn(u.x, __ddiv_rn(react_g(u.x, rhs.x, S.factor, a.inv_eps2, a.nu_exp),
-                                                   react_dg(u.x, S.factor, a.inv_eps2, a.nu_exp)));
-                    u.y = __dsub_rn(u.y, __ddiv_rn(react_g(u.y, rhs.y, S.factor, a.inv_eps2, a.nu_exp),
-                                                   react_dg(u.y, S.factor, a.inv_eps2, a.nu_exp)));
-                    st2(S.u + 2 * i, u);
+                    u = qmap([&](int e) {
+                        const double v = qe(u, e), r = qe(rhs, e);
+                        return __dsub_rn(v, __ddiv_rn(react_g(v, r, S.factor, a.inv_eps2, a.nu_exp),
+                                                      react_dg(v, S.factor, a.inv_eps2, a.nu_exp)));
+                    });
+                    stq(S.u, i, u, full);
                 }
-                gmax = absmax_nan(gmax, react_g(u.x, rhs.x, S.factor, a.inv_eps2, a.nu_exp));
-                gmax = absmax_nan(gmax, react_g(u.y, rhs.y, S.factor, a.inv_eps2, a.nu_exp));
-            }
+                for (int e = 0; e < (full ? 4 : 2); ++e)
+                    gmax = absmax_nan(gmax, react_g(qe(u, e), qe(rhs, e), S.factor, a.inv_eps2, a.nu_exp));
+            });
             gmax = block_max(gmax, scratch);
             put_partial(a.partials, slot, b, gmax);
         }
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) reaction_newton_kernel(const __grid_
     }
 }
 
-constexpr int kReactMaxGrid = 148 * 8;
+constexpr int kReactMaxGrid = kMaxGrid;
 
 }  // namespace
 }  // namespace sdcb200
