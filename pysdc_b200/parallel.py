@@ -316,3 +316,26 @@ class SlabComm(TorchComm):
         send/recv).  At the ends of a non-periodic domain the halo planes keep their zeros (= the Dirichlet value)."""
         self.exchange_planes([(f._lay.plane(f._buf, f._lay.nz - 1), f._lay.plane(f._buf, -1), f._lay.plane(f._buf, 0),
                                f._lay.plane(f._buf, f._lay.nz)) for f in fields], periodic)
+
+
+def cartesian_comms(n_outer, n_space, device=None):
+    """Two-dimensional process grid over ALL ranks of the job (world = n_outer * n_space, rank = outer * n_space + space):
+    returns ``(outer_comm, space_comm)`` of this rank - ``outer_comm`` (a ``TorchComm``) joins the ranks with the same
+    space index (time slices of PFASST, or the collocation nodes of the node-parallel sweepers), ``space_comm`` (a
+    ``SlabComm``) the ranks of one outer index, i.e. the slabs of one field.  torch.distributed creates groups
+    collectively over the default group, so every rank builds every group here, in the same order (this is how a
+    communicator that does not span the job gets its sub-communicators: up front, not by splitting it later)."""
+    world = dist.get_world_size()
+    if n_outer * n_space != world:
+        raise ValueError(f"{n_outer} x {n_space} ranks requested, the job has {world}")
+    rank = dist.get_rank()
+    outer_comm = space_comm = None
+    for o in range(n_outer):
+        g = dist.new_group(ranks=[o * n_space + s for s in range(n_space)])
+        if rank // n_space == o:
+            space_comm = SlabComm(g, device)
+    for s_ in range(n_space):
+        g = dist.new_group(ranks=[o * n_space + s_ for o in range(n_outer)])
+        if rank % n_space == s_:
+            outer_comm = TorchComm(g, device)
+    return outer_comm, space_comm

@@ -552,6 +552,9 @@ class NodeParallelMixin:
         from .comm import MAX
 
         self._tc.allreduce_device(norms, MAX)  # every rank gets all M node norms: one collective, then one read
+        space = L.u[0].comm  # nodes x slabs: the norms of a node are maxima over the slabs of its field as well
+        if space is not None and getattr(space, "size", 1) > 1 and hasattr(space, "allreduce_device"):
+            space.allreduce_device(norms, MAX)
         host = norms.cpu().tolist()
         res = max(host[:M]) if rtype.startswith("full") else host[M - 1]
         L.status.residual = res / host[M] if rtype.endswith("_rel") else res

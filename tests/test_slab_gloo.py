@@ -180,3 +180,78 @@ def test_split_planes():
     assert split_planes(511, 8) == [64] * 7 + [63]
     assert split_planes(511, 1) == [511]
     assert sum(split_planes(127, 3)) == 127
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nodes x slabs: the node-parallel sweeper (one collocation node per outer rank) on slab-decomposed fields, i.e. a
+# 2-D process grid built with parallel.cartesian_comms - against the single-process run
+# ---------------------------------------------------------------------------------------------------------------------
+def _grid_worker(rank, world, port, n, n_nodes, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_backend import NumpyBackend
+        from pysdc_b200 import backend
+        from pysdc_b200.controller import controller_nonMPI
+        from pysdc_b200.parallel import cartesian_comms
+        from pysdc_b200.problems import heatNd_unforced
+        from pysdc_b200.stats import get_sorted
+        from pysdc_b200.sweepers import generic_implicit_MPI
+
+        backend.set_backend(NumpyBackend())
+        node_comm, space_comm = cartesian_comms(n_nodes, world // n_nodes)
+        assert node_comm.size == n_nodes and space_comm.size == world // n_nodes
+        assert node_comm.rank == rank // space_comm.size and space_comm.rank == rank % space_comm.size
+        sp = _spec(n)
+        c = controller_nonMPI(1, {"logger_level": 40}, dict(
+            problem_class=heatNd_unforced, problem_params=dict(sp["problem_params"], comm=space_comm),
+            sweeper_class=generic_implicit_MPI,
+            sweeper_params=dict(sp["sweeper_params"], num_nodes=n_nodes, comm=node_comm),
+            level_params=sp["level_params"], step_params=sp["step_params"]))
+        P = c.MS[0].levels[0].prob
+        u0 = P.dtype_u(P.init)
+        u0[:] = np.random.default_rng(1234).standard_normal((n, n, n))
+        uend, stats = c.run(u0=u0, t0=0.0, Tend=2e-3)
+        np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.gather())
+        np.save(os.path.join(out_dir, f"niter_{rank}.npy"), np.array([v for _, v in get_sorted(stats, type="niter")]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nodes_times_slabs_matches_serial(tmp_path):
+    from conftest import free_port
+
+    n, n_nodes, world = 13, 2, 4
+    mp.spawn(_grid_worker, args=(world, free_port(), n, n_nodes, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_backend import NumpyBackend
+    from pysdc_b200 import backend
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.datatypes import mesh
+    from pysdc_b200.problems import heatNd_unforced
+    from pysdc_b200.stats import get_sorted
+    from pysdc_b200.sweepers import generic_implicit
+
+    old, old_comm = backend._backend, mesh.comm
+    backend.set_backend(NumpyBackend())
+    try:
+        mesh.comm = None
+        sp = _spec(n)
+        c = controller_nonMPI(1, {"logger_level": 40}, dict(
+            problem_class=heatNd_unforced, problem_params=sp["problem_params"], sweeper_class=generic_implicit,
+            sweeper_params=dict(sp["sweeper_params"], num_nodes=n_nodes), level_params=sp["level_params"],
+            step_params=sp["step_params"]))
+        P = c.MS[0].levels[0].prob
+        u0 = P.dtype_u(P.init)
+        u0[:] = np.random.default_rng(1234).standard_normal((n, n, n))
+        uend, stats = c.run(u0=u0, t0=0.0, Tend=2e-3)
+        ref, niter = uend.get(), [v for _, v in get_sorted(stats, type="niter")]
+        for r in range(world):
+            got = np.load(os.path.join(tmp_path, f"uend_{r}.npy"))
+            assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+            assert list(np.load(os.path.join(tmp_path, f"niter_{r}.npy"))) == niter
+    finally:
+        backend.set_backend(old)
+        mesh.comm = old_comm
