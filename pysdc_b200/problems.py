@@ -773,7 +773,7 @@ class _TwoSolves:
                            "solve_system_2 (multi_implicit sweeper)")
 
     def solve_system_batch(self, rhs, factors, xs, ts=None):
-        self.solve_system(None, None, None, None)
+        self.solve_system(rhs, factors, xs, ts)  # same error for the batched entry of the single-solve sweepers
 
 
 class AllenCahnMultiMixin(_TwoSolves, AllenCahnSemiMixin):

@@ -446,7 +446,7 @@ class NodeParallelMixin:
     def _gathered_inputs(self, L):
         ins = []
         for f in self._all_f(L):
-            ins += [f.impl.flat, f.expl.flat] if self.imex else [f.flat]
+            ins += [getattr(f, self._comps[0]).flat, getattr(f, self._comps[1]).flat] if self.imex else [f.flat]
         return ins
 
     # ---- predictor (generic_implicit_MPI.py:124-157) ----------------------------------------------------------------
