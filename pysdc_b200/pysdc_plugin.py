@@ -17,9 +17,13 @@ from . import sweepers as _sweepers
 from .datatypes import comp2_mesh, imex_mesh, mesh  # noqa: F401
 from .transfer import mesh_to_mesh  # noqa: F401  (space_transfer_class for multi-level runs)
 
+# the reference's CuPy datatypes (datatype_classes/cupy_mesh.py), for scripts written against its GPU problem classes
+# (problem_classes/HeatEquation_ND_FD_CuPy.py, AllenCahn_2D_FD_gpu.py: same class names as the CPU ones)
+cupy_mesh, imex_cupy_mesh, comp2_cupy_mesh = mesh, imex_mesh, comp2_mesh
+
 globals().update({k: v for k, v in _problems._bind(_PySDCProblem).items()})
 globals().update({k: v for k, v in _sweepers._bind(_PySDCSweeper).items()})
 
-__all__ = ["mesh", "imex_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "allencahn_semiimplicit",
+__all__ = ["mesh", "imex_mesh", "comp2_mesh", "cupy_mesh", "imex_cupy_mesh", "comp2_cupy_mesh", "heatNd_unforced", "heatNd_forced", "allencahn_fullyimplicit", "allencahn_semiimplicit",
            "allencahn_semiimplicit_v2", "allencahn_multiimplicit", "allencahn_multiimplicit_v2", "multi_implicit", "generic_implicit", "imex_1st_order", "generic_implicit_MPI", "imex_1st_order_MPI",
            "mesh_to_mesh"]
