@@ -3,7 +3,8 @@
 
 TEST INFRASTRUCTURE.  pySDC is pure Python; "building" it means making its package importable where
 ``/root/reference`` does not exist.  This recipe copies the reference's own ``pySDC/{core,helpers,implementations}``
-(1.7 MB; projects, playgrounds, tutorials and the reference's tests are not needed by the sweep path) byte for byte from
+(1.7 MB) plus its tutorials and the few reference tests that exercise the classes on the path (0.4 MB; projects and
+playgrounds are not needed) byte for byte from
 where they lie under ``/root/reference`` into ``oracle/_ref/pySDC``.  ``oracle/_ref/`` is git-ignored (reference sources
 never enter the history) but not gpurun-ignored, so the copy travels to the GPU box like a built ``.so``.  A manifest
 with one SHA-256 per file is written next to it; ``verify()`` re-checks it, which is how the tests on the GPU box know
@@ -27,7 +28,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("PYSDC_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
-PARTS = ["__init__.py", "core", "helpers", "implementations"]
+PARTS = ["__init__.py", "core", "helpers", "implementations",
+         # the reference's own tutorials and the tests of them / of the classes on the path: tests/test_reference_suite.py
+         # runs them, unmodified, on the plug-in classes
+         "tutorial", "tests/__init__.py", "tests/test_tutorials", "tests/test_transfer_classes/test_mesh_to_mesh.py",
+         "tests/test_2d_fd_accuracy.py"]
 MANIFEST = os.path.join(DST, "MANIFEST.json")
 
 
@@ -55,8 +60,9 @@ def build():
     os.makedirs(pkg)
     for part in PARTS:
         s, d = os.path.join(src, part), os.path.join(pkg, part)
+        os.makedirs(os.path.dirname(d), exist_ok=True)
         if os.path.isdir(s):
-            shutil.copytree(s, d, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
+            shutil.copytree(s, d, ignore=shutil.ignore_patterns("__pycache__", "*.pyc", "data"))
         else:
             shutil.copy2(s, d)
     for extra in ("LICENSE",):

@@ -126,6 +126,56 @@ def fd_operator_tables(derivative, order, stencil_type, bc, dx, coeff):
     return tables
 
 
+def sparse_operator(tables, n, ndim, periodic):
+    """The spatial operator as a scipy sparse matrix on the host - the attribute ``A`` of the reference's problem classes
+    (generic_ND_FD.py:140-149; Kronecker sum of helpers/problem_helper.py:226-239), assembled from the same 1-D tables
+    the kernels use.  Set-up / analysis aid only (tutorial/step_1/C builds the collocation matrix from it); the sweep
+    never touches it."""
+    import scipy.sparse as sp
+
+    h, coef = tables["h"], np.asarray(tables["coef"], dtype=float)
+    A1 = sp.lil_matrix((n, n))
+    for i in range(n):
+        if not periodic and i < h:
+            row = np.asarray(tables["lo"])[i]
+            for j in range(min(2 * h + 1, n)):
+                A1[i, j] = row[j]
+        elif not periodic and i >= n - h:
+            row = np.asarray(tables["hi"])[n - 1 - i]
+            for j in range(min(2 * h + 1, n)):
+                A1[i, n - (2 * h + 1) + j] = row[j]
+        else:
+            for k in range(-h, h + 1):
+                if coef[k + h] != 0.0:
+                    A1[i, (i + k) % n] += coef[k + h]
+    A1 = A1.tocsc()
+    if ndim == 1:
+        return A1
+    if ndim == 2:
+        return (sp.kron(A1, sp.eye(n)) + sp.kron(sp.eye(n), A1)).tocsc()
+    return (sp.kron(A1, sp.eye(n**2)) + sp.kron(sp.eye(n**2), A1) + sp.kron(sp.kron(sp.eye(n), A1), sp.eye(n))).tocsc()
+
+
+class _HostOperator:
+    """``A`` and ``Id`` of the reference's finite-difference problem classes, built on first use."""
+
+    def _operator_tables(self):
+        raise NotImplementedError
+
+    @property
+    def A(self):
+        if "_A_host" not in self.__dict__:
+            self.__dict__["_A_host"] = sparse_operator(self._operator_tables(), self.nvars[0], len(self.nvars),
+                                                       self.bc == "periodic")
+        return self.__dict__["_A_host"]
+
+    @property
+    def Id(self):
+        import scipy.sparse as sp
+
+        return sp.eye(int(np.prod(self.nvars)), format="csc")
+
+
 def check_fd_params(nvars, freq, bc):
     """Parameter checks of GenericNDimFinDiff (generic_ND_FD.py:99-133); returns (nvars, freq, ndim, bc)."""
     if type(nvars) not in [int, tuple]:
@@ -182,7 +232,7 @@ class DeviceWorkCounter:
 # ---------------------------------------------------------------------------------------------------------------------
 # heat equation
 # ---------------------------------------------------------------------------------------------------------------------
-class HeatMixin(OutputMixin):
+class HeatMixin(_HostOperator, OutputMixin):
     dtype_u = mesh
     dtype_f = mesh
     forced = False
@@ -202,9 +252,8 @@ class HeatMixin(OutputMixin):
         if order not in (2, 4, 6, 8) or stencil_type != "center":
             raise ProblemError("the device stencils are the centred Laplacians of order 2, 4, 6 and 8; "
                                f"got order={order}, stencil_type={stencil_type!r}")
-        if order != 2 and (solver_type == "direct" or preconditioner is not None or comm is not None):
-            raise ProblemError("order > 2 is implemented with solver_type='CG' or 'GMRES', without preconditioner and "
-                               "on one GPU")
+        if order != 2 and (preconditioner is not None or comm is not None):
+            raise ProblemError("order > 2 is implemented without preconditioner and on one GPU")
         if order != 2 and any(nv <= order for nv in nvars):
             raise ProblemError(f"grid too small for the order-{order} stencil")
         if solver_type not in ("CG", "GMRES", "direct"):
@@ -212,8 +261,10 @@ class HeatMixin(OutputMixin):
                                "'direct')")
         if solver_type == "GMRES" and (preconditioner is not None or comm is not None):
             raise ProblemError("solver_type='GMRES' runs without preconditioner and on one GPU")
-        if solver_type == "direct" and ndim > 1:
-            raise ProblemError("solver_type='direct' is implemented on the device for 1-D grids only; use 'CG'")
+        # solver_type='direct' (the reference's default) exists on the device for 1-D order-2 grids; elsewhere the problem
+        # can still be set up and evaluated (eval_f, u_exact, transfers: the reference's accuracy tests and tutorials do
+        # just that) and the first solve raises
+        self._direct_ok = ndim == 1 and order == 2
 
         if preconditioner not in (None, "chebyshev"):
             raise ProblemError(f"unknown preconditioner {preconditioner!r} (have None, 'chebyshev')")
@@ -254,6 +305,9 @@ class HeatMixin(OutputMixin):
             self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
 
     # -- reference attributes -----------------------------------------------------------------------------------------
+    def _operator_tables(self):
+        return fd_operator_tables(2, self.order, self.stencil_type, self.bc, self.dx, self.nu)
+
     @property
     def ndim(self):
         return len(self.nvars)
@@ -341,6 +395,9 @@ class HeatMixin(OutputMixin):
         m_diag = [1.0 - f * self.a_diag for f in factors]
         m_off = [-(f * self.a_off) for f in factors]
         if self.solver_type == "direct":
+            if not self._direct_ok:
+                raise ProblemError("solver_type='direct' is implemented on the device for 1-D order-2 grids only; use "
+                                   "'CG' or 'GMRES'")
             self._be.heat_direct_solve_1d(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs],
                                           [x.flat for x in xs])
             return
@@ -428,7 +485,7 @@ class HeatForcedMixin(HeatMixin):
 # ---------------------------------------------------------------------------------------------------------------------
 # advection equation
 # ---------------------------------------------------------------------------------------------------------------------
-class AdvectionMixin(OutputMixin):
+class AdvectionMixin(_HostOperator, OutputMixin):
     """``advectionNd`` (problem_classes/AdvectionEquation_ND_FD.py:7-164 on top of ``GenericNDimFinDiff``): u_t = -c
     grad u in 1-3 dimensions, any stencil of helpers/problem_helper.py:4-39 within four grid points (centred order 2-8,
     upwind order 1-5, forward / backward order 1-4), ``eval_f`` by the general finite-difference kernel and the node
@@ -444,7 +501,7 @@ class AdvectionMixin(OutputMixin):
         nvars, freq, ndim, bc = check_fd_params(nvars, freq, bc)
         if bc not in BC_CODES:
             raise ProblemError(f"boundary condition {bc!r} is not implemented on the device (have {list(BC_CODES)})")
-        if solver_type != "GMRES":
+        if solver_type not in ("GMRES", "direct", "CG"):
             raise ProblemError(f"solver_type {solver_type!r} is not implemented on the device for the advection "
                                "equation: its systems are non-symmetric, use solver_type='GMRES'")
         try:
@@ -471,6 +528,9 @@ class AdvectionMixin(OutputMixin):
         self._work = None
         self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
 
+    def _operator_tables(self):
+        return self._fd
+
     ndim = HeatMixin.ndim
     dx = HeatMixin.dx
     grids = HeatMixin.grids
@@ -488,6 +548,9 @@ class AdvectionMixin(OutputMixin):
     def solve_system_batch(self, rhs, factors, xs, ts=None):
         """(I - factors[i] A) xs[i] = rhs[i] in place by restarted GMRES (generic_ND_FD.py:241-250), one persistent
         launch per system."""
+        if self.solver_type != "GMRES":  # the problem can be set up and evaluated with any solver_type; solves need GMRES
+            raise ProblemError(f"solver_type {self.solver_type!r} is not implemented on the device for the advection "
+                               "equation: its systems are non-symmetric, use solver_type='GMRES'")
         if self._work is None:
             self._work = self._be.fd_gmres_workspace(self._lay, GMRES_RESTART)
         counter = self._counters[1:2]

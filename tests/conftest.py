@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    for name in ("base", "mpi4py", "cupy", "slow", "benchmark"):  # marks of the reference's own tests (test_reference_suite.py)
+        config.addinivalue_line("markers", f"{name}: mark used by the reference's test-suite")
 
 
 def pytest_collection_modifyitems(config, items):

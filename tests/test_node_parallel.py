@@ -136,9 +136,9 @@ def _check(tmp_path, name, kind, mode):
         assert np.all(np.abs(np.array(outs[r]["work_CG"]) - want) <= slack), (r, outs[r]["work_CG"], want)
 
 
-def _variants(cuda_cases):
-    """(name, kind) pairs: every case on the numpy double (CPU suite), ``cuda_cases`` of them on the real kernels."""
-    return [(n, "numpy") for n in CASES] + [pytest.param(n, "cuda", marks=pytest.mark.gpu) for n in cuda_cases]
+def _variants(cuda_cases, numpy_cases=CASES):
+    """(name, kind) pairs: ``numpy_cases`` on the numpy double (CPU suite), ``cuda_cases`` on the real kernels."""
+    return [(n, "numpy") for n in numpy_cases] + [pytest.param(n, "cuda", marks=pytest.mark.gpu) for n in cuda_cases]
 
 
 @pytest.mark.parametrize("name,kind", _variants(CASES))
@@ -147,13 +147,13 @@ def test_node_parallel_sweepers_standalone(tmp_path, name, kind):
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("name,kind", _variants(CASES[2:]))
+@pytest.mark.parametrize("name,kind", _variants(CASES[2:], CASES[1:]))
 def test_node_parallel_sweepers_under_the_reference_controller(tmp_path, name, kind):
     _check(tmp_path, name, kind, "plugin")
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("name,kind", _variants(CASES[1:2]))
+@pytest.mark.parametrize("name,kind", _variants(CASES[1:2], CASES[:2]))
 def test_reference_node_parallel_sweepers_on_the_facade(tmp_path, name, kind):
     _check(tmp_path, name, kind, "reference")
 

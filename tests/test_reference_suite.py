@@ -1,0 +1,137 @@
+"""The reference's OWN tests and tutorials, unmodified, on the plug-in classes.
+
+``pySDC/tests/test_tutorials/test_step_{1..6}.py`` (tutorial steps 1-6 with the asserts pySDC ships: spatial and
+collocation accuracy, iteration counts of SDC / MLSDC / PFASST, ...), ``tests/test_transfer_classes/test_mesh_to_mesh.py``
+and ``tests/test_2d_fd_accuracy.py`` are imported from the reference tree (or its shipped copy ``oracle/_ref``) and their
+test functions are called as they are.  The only change is WHERE the class names resolve: for the duration of a test the
+modules ``pySDC.implementations.problem_classes.{HeatEquation_ND_FD, AdvectionEquation_ND_FD, AllenCahn_2D_FD}``,
+``sweeper_classes.{generic_implicit, imex_1st_order, multi_implicit}``, ``transfer_classes.TransferMesh`` and
+``datatype_classes.mesh`` are replaced by modules that export the classes of ``pysdc_b200.pysdc_plugin`` — the two
+changed import lines of INTEGRATION.md, applied to the reference's own test-suite.  Controller, Step / Level,
+collocation, hooks, statistics and the tutorials' own code stay the reference's.
+
+``numpy`` variants: kernel library replaced by the numpy test double (CPU suite); ``cuda`` variants (``-m gpu``): the
+real CUDA kernels.  Not run: tutorial tests that need classes outside the path (Penning trap: step 3 B/C, 4 D), the
+``mpirun`` launcher (6 C), and step 5 C (advection with ``solver_type='direct'``: the device has GMRES only).
+``matplotlib`` is absent from the image; the tutorials only plot with it, so a do-nothing stand-in is installed."""
+import importlib
+import os
+import sys
+import types
+from unittest import mock
+
+import pytest
+
+from conftest import reference_paths
+
+REF_PATHS = reference_paths()
+pytestmark = pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+
+SWAPPED = {
+    "pySDC.implementations.problem_classes.HeatEquation_ND_FD": ["heatNd_unforced", "heatNd_forced"],
+    "pySDC.implementations.problem_classes.AdvectionEquation_ND_FD": ["advectionNd"],
+    "pySDC.implementations.problem_classes.AllenCahn_2D_FD": [
+        "allencahn_fullyimplicit", "allencahn_semiimplicit", "allencahn_semiimplicit_v2", "allencahn_multiimplicit",
+        "allencahn_multiimplicit_v2"],
+    "pySDC.implementations.sweeper_classes.generic_implicit": ["generic_implicit"],
+    "pySDC.implementations.sweeper_classes.imex_1st_order": ["imex_1st_order"],
+    "pySDC.implementations.sweeper_classes.multi_implicit": ["multi_implicit"],
+    "pySDC.implementations.transfer_classes.TransferMesh": ["mesh_to_mesh"],
+    "pySDC.implementations.datatype_classes.mesh": ["mesh", "imex_mesh", "comp2_mesh"],
+}
+
+REFERENCE_TESTS = [
+    ("pySDC.tests.test_tutorials.test_step_1", "test_A"), ("pySDC.tests.test_tutorials.test_step_1", "test_B"),
+    ("pySDC.tests.test_tutorials.test_step_1", "test_C"), ("pySDC.tests.test_tutorials.test_step_1", "test_D"),
+    ("pySDC.tests.test_tutorials.test_step_2", "test_A"), ("pySDC.tests.test_tutorials.test_step_2", "test_B"),
+    ("pySDC.tests.test_tutorials.test_step_2", "test_C"), ("pySDC.tests.test_tutorials.test_step_3", "test_A"),
+    ("pySDC.tests.test_tutorials.test_step_4", "test_A"), ("pySDC.tests.test_tutorials.test_step_4", "test_B"),
+    ("pySDC.tests.test_tutorials.test_step_4", "test_C"), ("pySDC.tests.test_tutorials.test_step_5", "test_A"),
+    ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
+    ("pySDC.tests.test_tutorials.test_step_6", "test_B"),
+    ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_dirichlet"),
+    ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_periodic"),
+    ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_2d_periodic"),
+    ("pySDC.tests.test_2d_fd_accuracy", "test_spatial_accuracy"),
+]
+# on the GPU: one test per kind of run (collocation set-up, SDC through the front end, MLSDC, PFASST, transfer orders)
+ON_GPU = {("pySDC.tests.test_tutorials.test_step_1", "test_B"), ("pySDC.tests.test_tutorials.test_step_2", "test_C"),
+          ("pySDC.tests.test_tutorials.test_step_3", "test_A"), ("pySDC.tests.test_tutorials.test_step_4", "test_C"),
+          ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
+          ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_2d_periodic")}
+
+
+SETUP_ONLY = {("pySDC.tests.test_tutorials.test_step_1", "test_C"), ("pySDC.tests.test_tutorials.test_step_1", "test_D"),
+              ("pySDC.tests.test_tutorials.test_step_4", "test_B"), ("pySDC.tests.test_tutorials.test_step_5", "test_A")}
+
+
+def _is_scratch(name):
+    return name.startswith(("pySDC.tutorial", "pySDC.tests")) or name == "matplotlib" or name.startswith("matplotlib.")
+
+
+@pytest.fixture
+def swapped_reference(request, tmp_path, monkeypatch):
+    """The reference importable, its modules of the path replaced by plug-in exports, cwd = a scratch directory (the
+    tutorials write their output to ./data); everything is undone afterwards so that other tests see the real modules."""
+    for p in reversed(REF_PATHS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from pysdc_b200 import backend
+
+    old_backend = backend._backend
+    if request.param == "cuda":
+        backend.set_backend(backend.CudaBackend())
+    else:
+        from fake_backend import NumpyBackend
+
+        backend.set_backend(NumpyBackend())
+    from pysdc_b200 import pysdc_plugin as plugin
+
+    saved = {k: sys.modules.get(k) for k in SWAPPED}
+    stale = [k for k in sys.modules if _is_scratch(k)]
+    for k in stale:  # tutorial modules bind the class names at import time: they have to be imported afresh
+        del sys.modules[k]
+    for name, exports in SWAPPED.items():
+        mod = types.ModuleType(name)
+        mod.__doc__ = "plug-in classes of pysdc_b200 under the reference's module name (tests/test_reference_suite.py)"
+        for e in exports:
+            setattr(mod, e, getattr(plugin, e))
+        sys.modules[name] = mod
+    if importlib.util.find_spec("matplotlib") is None:
+        fake = mock.MagicMock(name="matplotlib")
+        for plt in (fake.pyplot, fake.pylab):  # the tutorials assert that the figure file exists
+            plt.savefig.side_effect = lambda fname, *a, **k: open(fname, "wb").close()
+        sys.modules.update({"matplotlib": fake, "matplotlib.pyplot": fake.pyplot, "matplotlib.pylab": fake.pylab})
+    monkeypatch.chdir(tmp_path)
+    os.makedirs(os.path.join(tmp_path, "data"), exist_ok=True)
+    try:
+        yield plugin
+    finally:
+        for k in [k for k in sys.modules if _is_scratch(k)]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        backend.set_backend(old_backend)
+
+
+def _params():
+    out = []
+    for mod, fn in REFERENCE_TESTS:
+        tag = f"{mod.split('.')[-1]}::{fn}"
+        out.append(pytest.param("numpy", mod, fn, id=f"numpy-{tag}"))
+        if (mod, fn) in ON_GPU:
+            out.append(pytest.param("cuda", mod, fn, id=f"cuda-{tag}", marks=pytest.mark.gpu))
+    return out
+
+
+@pytest.mark.parametrize("swapped_reference,module,function", _params(), indirect=["swapped_reference"])
+def test_reference_test_passes_on_plugin_classes(swapped_reference, module, function):
+    from pysdc_b200 import backend
+
+    launches0 = backend.get_backend().launches
+    getattr(importlib.import_module(module), function)()
+    # the test really went through the device classes (set-up-only tutorials launch nothing: u_exact is a host expression)
+    assert backend.get_backend().launches > launches0 or (module, function) in SETUP_ONLY
