@@ -261,9 +261,8 @@ class HeatMixin(_HostOperator, OutputMixin):
                                "'direct')")
         if solver_type == "GMRES" and (preconditioner is not None or comm is not None):
             raise ProblemError("solver_type='GMRES' runs without preconditioner and on one GPU")
-        # solver_type='direct' (the reference's default) exists on the device for 1-D order-2 grids; elsewhere the problem
-        # can still be set up and evaluated (eval_f, u_exact, transfers: the reference's accuracy tests and tutorials do
-        # just that) and the first solve raises
+        # solver_type='direct' (the reference's default): a device factorisation exists for 1-D order-2 grids (tridiagonal
+        # Thomas solve); every other grid runs the CG down to its attainable accuracy instead (solve_system_batch)
         self._direct_ok = ndim == 1 and order == 2
 
         if preconditioner not in (None, "chebyshev"):
@@ -394,12 +393,23 @@ class HeatMixin(_HostOperator, OutputMixin):
         persistent launch."""
         m_diag = [1.0 - f * self.a_diag for f in factors]
         m_off = [-(f * self.a_off) for f in factors]
-        if self.solver_type == "direct":
-            if not self._direct_ok:
-                raise ProblemError("solver_type='direct' is implemented on the device for 1-D order-2 grids only; use "
-                                   "'CG' or 'GMRES'")
+        if self.solver_type == "direct" and self._direct_ok:
             self._be.heat_direct_solve_1d(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs],
                                           [x.flat for x in xs])
+            return
+        if self.solver_type == "direct":
+            # no device factorisation beyond the 1-D order-2 tridiagonal one: the system is solved by the persistent CG
+            # iterated down to the accuracy the floating-point recurrence can attain (rtol 1e-15 on the recurrence
+            # residual, the same forward error ~ cond * eps a sparse direct solve leaves); like the reference's 'direct'
+            # it counts no work (generic_ND_FD.py:236-239)
+            scratch = self._counters[2: 2 + len(xs)]
+            n_total = int(np.prod(self.nvars))
+            if self._ho is not None:
+                self._be.heat_cg_solve_ho(self._lay, self._bc, self._ho, list(factors), [r.flat for r in rhs],
+                                          [x.flat for x in xs], 1e-15, 10 * n_total, self._cg_work(len(xs)), scratch)
+            else:
+                self._be.heat_cg_solve(self._lay, self._bc, m_diag, m_off, [r.flat for r in rhs], [x.flat for x in xs],
+                                       1e-15, 10 * n_total, self._cg_work(len(xs)), scratch)
             return
         counters = self._counters[2: 2 + len(xs)]
         counters.zero_()

@@ -1,8 +1,8 @@
 """The reference's OWN tests and tutorials, unmodified, on the plug-in classes.
 
 ``pySDC/tests/test_tutorials/test_step_{1..6}.py`` (tutorial steps 1-6 with the asserts pySDC ships: spatial and
-collocation accuracy, iteration counts of SDC / MLSDC / PFASST, ...), ``tests/test_transfer_classes/test_mesh_to_mesh.py``
-and ``tests/test_2d_fd_accuracy.py`` are imported from the reference tree (or its shipped copy ``oracle/_ref``) and their
+collocation accuracy, iteration counts of SDC / MLSDC / PFASST, ...), ``tests/test_transfer_classes/test_mesh_to_mesh.py``,
+``tests/test_2d_fd_accuracy.py`` and ``tests/test_convergence_controllers/test_check_convergence.py`` are imported from the reference tree (or its shipped copy ``oracle/_ref``) and their
 test functions are called as they are.  The only change is WHERE the class names resolve: for the duration of a test the
 modules ``pySDC.implementations.problem_classes.{HeatEquation_ND_FD, AdvectionEquation_ND_FD, AllenCahn_2D_FD}``,
 ``sweeper_classes.{generic_implicit, imex_1st_order, multi_implicit}``, ``transfer_classes.TransferMesh`` and
@@ -53,12 +53,26 @@ REFERENCE_TESTS = [
     ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_periodic"),
     ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_2d_periodic"),
     ("pySDC.tests.test_2d_fd_accuracy", "test_spatial_accuracy"),
+    # convergence_controller_classes/check_convergence.py on a 1-D periodic order-6 heat problem with the 'direct' solver
+    # (parametrised in the reference: the arguments are its own parameter lists; "gpu-only": thousands of CG iterations
+    # per solve stand in for the 'direct' solver, which the numpy test double takes minutes for)
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=1)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=5)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=50), "gpu-only"),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-3)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-5), "gpu-only"),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-10), "gpu-only"),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_residual", dict(restol=1e-3)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_residual", dict(restol=1e-5), "gpu-only"),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_residual", dict(restol=1e-10), "gpu-only"),
 ]
 # on the GPU: one test per kind of run (collocation set-up, SDC through the front end, MLSDC, PFASST, transfer orders)
 ON_GPU = {("pySDC.tests.test_tutorials.test_step_1", "test_B"), ("pySDC.tests.test_tutorials.test_step_2", "test_C"),
           ("pySDC.tests.test_tutorials.test_step_3", "test_A"), ("pySDC.tests.test_tutorials.test_step_4", "test_C"),
           ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
-          ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_2d_periodic")}
+          ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_2d_periodic"),
+          ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment"),
+          ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_residual")}
 
 
 SETUP_ONLY = {("pySDC.tests.test_tutorials.test_step_1", "test_C"), ("pySDC.tests.test_tutorials.test_step_1", "test_D"),
@@ -119,19 +133,21 @@ def swapped_reference(request, tmp_path, monkeypatch):
 
 def _params():
     out = []
-    for mod, fn in REFERENCE_TESTS:
-        tag = f"{mod.split('.')[-1]}::{fn}"
-        out.append(pytest.param("numpy", mod, fn, id=f"numpy-{tag}"))
-        if (mod, fn) in ON_GPU:
-            out.append(pytest.param("cuda", mod, fn, id=f"cuda-{tag}", marks=pytest.mark.gpu))
+    for mod, fn, *rest in REFERENCE_TESTS:
+        kwargs = rest[0] if rest else {}
+        tag = f"{mod.split('.')[-1]}::{fn}" + "".join(f"-{v}" for v in kwargs.values())
+        if "gpu-only" not in rest:
+            out.append(pytest.param("numpy", mod, fn, kwargs, id=f"numpy-{tag}"))
+        if (mod, fn) in ON_GPU or "gpu-only" in rest:
+            out.append(pytest.param("cuda", mod, fn, kwargs, id=f"cuda-{tag}", marks=pytest.mark.gpu))
     return out
 
 
-@pytest.mark.parametrize("swapped_reference,module,function", _params(), indirect=["swapped_reference"])
-def test_reference_test_passes_on_plugin_classes(swapped_reference, module, function):
+@pytest.mark.parametrize("swapped_reference,module,function,kwargs", _params(), indirect=["swapped_reference"])
+def test_reference_test_passes_on_plugin_classes(swapped_reference, module, function, kwargs):
     from pysdc_b200 import backend
 
     launches0 = backend.get_backend().launches
-    getattr(importlib.import_module(module), function)()
+    getattr(importlib.import_module(module), function)(**kwargs)
     # the test really went through the device classes (set-up-only tutorials launch nothing: u_exact is a host expression)
     assert backend.get_backend().launches > launches0 or (module, function) in SETUP_ONLY
