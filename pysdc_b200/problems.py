@@ -536,7 +536,8 @@ class AdvectionMixin(_HostOperator, OutputMixin):
         self._fd = fd_operator_tables(1, order, stencil_type, bc, dx, -c)  # AdvectionEquation_ND_FD.py:89: coeff = -c
         self._counters = self._be.zeros(2, dtype=torch.int32)  # [total GMRES its, its of the current solve]
         self._work = None
-        self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
+        if solver_type != "direct":
+            self.work_counters[solver_type] = DeviceWorkCounter(self._counters[0:1])
 
     def _operator_tables(self):
         return self._fd
@@ -558,16 +559,22 @@ class AdvectionMixin(_HostOperator, OutputMixin):
     def solve_system_batch(self, rhs, factors, xs, ts=None):
         """(I - factors[i] A) xs[i] = rhs[i] in place by restarted GMRES (generic_ND_FD.py:241-250), one persistent
         launch per system."""
-        if self.solver_type != "GMRES":  # the problem can be set up and evaluated with any solver_type; solves need GMRES
-            raise ProblemError(f"solver_type {self.solver_type!r} is not implemented on the device for the advection "
-                               "equation: its systems are non-symmetric, use solver_type='GMRES'")
+        if self.solver_type == "CG":  # the problem can be set up and evaluated with it; the systems are non-symmetric
+            raise ProblemError("solver_type 'CG' is not implemented on the device for the advection equation: its systems "
+                               "are non-symmetric, use solver_type='GMRES'")
         if self._work is None:
             self._work = self._be.fd_gmres_workspace(self._lay, GMRES_RESTART)
         counter = self._counters[1:2]
+        # solver_type='direct' (the reference's default): no device factorisation of these banded non-symmetric systems;
+        # the restarted GMRES is iterated down to a relative residual of 1e-14 instead and, like the reference's
+        # 'direct', counts no work
+        direct = self.solver_type == "direct"
+        rtol, cap = (1e-14, 50 * GMRES_RESTART) if direct else (self.lintol, self.liniter)
         for f, r, x in zip(factors, rhs, xs):
-            self._be.fd_gmres_solve(self._lay, self._bc, self._fd, f, r.flat, x.flat, self.lintol, self.liniter,
-                                    GMRES_RESTART, self._work, counter)
-        self._counters[0:1] += counter
+            self._be.fd_gmres_solve(self._lay, self._bc, self._fd, f, r.flat, x.flat, rtol, cap, GMRES_RESTART,
+                                    self._work, counter)
+        if not direct:
+            self._counters[0:1] += counter
         counter.zero_()
 
     def solve_system(self, rhs, factor, u0, t):

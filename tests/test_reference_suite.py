@@ -11,8 +11,9 @@ changed import lines of INTEGRATION.md, applied to the reference's own test-suit
 collocation, hooks, statistics and the tutorials' own code stay the reference's.
 
 ``numpy`` variants: kernel library replaced by the numpy test double (CPU suite); ``cuda`` variants (``-m gpu``): the
-real CUDA kernels.  Not run: tutorial tests that need classes outside the path (Penning trap: step 3 B/C, 4 D), the
-``mpirun`` launcher (6 C), and step 5 C (advection with ``solver_type='direct'``: the device has GMRES only).
+real CUDA kernels.  Not run: tutorial tests that need classes outside the path (Penning trap: step 3 B/C, 4 D), and the
+``mpirun`` launcher (6 C).  Step 5 C (advection, ``solver_type='direct'`` = GMRES to 1e-14 here) takes a minute on the numpy
+double and runs in the GPU suite only.
 ``matplotlib`` is absent from the image; the tutorials only plot with it, so a do-nothing stand-in is installed."""
 import importlib
 import os
@@ -47,7 +48,8 @@ REFERENCE_TESTS = [
     ("pySDC.tests.test_tutorials.test_step_2", "test_C"), ("pySDC.tests.test_tutorials.test_step_3", "test_A"),
     ("pySDC.tests.test_tutorials.test_step_4", "test_A"), ("pySDC.tests.test_tutorials.test_step_4", "test_B"),
     ("pySDC.tests.test_tutorials.test_step_4", "test_C"), ("pySDC.tests.test_tutorials.test_step_5", "test_A"),
-    ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
+    ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_5", "test_C", {}, "gpu-only"),
+    ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
     ("pySDC.tests.test_tutorials.test_step_6", "test_B"),
     ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_dirichlet"),
     ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_periodic"),
