@@ -407,10 +407,17 @@ class NodeParallelMixin:
     reference only ``L.u[rank+1]`` / ``L.f[rank+1]`` (and index 0) exist on a rank."""
 
     def __init__(self, params, level):
-        if "comm" not in params:  # generic_implicit_MPI.py:35-37 (MPI.COMM_WORLD)
-            from .parallel import TorchComm
+        if "comm" not in params:  # generic_implicit_MPI.py:35-37: MPI.COMM_WORLD - here the mpi4py-style communicator
+            # over all ranks of the torch.distributed job (other reference code, e.g. base_transfer_MPI, talks to it
+            # through the mpi4py surface: Reduce, Bcast, ...)
+            import sys
 
-            params["comm"] = TorchComm()
+            if "mpi4py.MPI" in sys.modules and hasattr(getattr(sys.modules["mpi4py.MPI"], "COMM_WORLD", None), "tc"):
+                params["comm"] = sys.modules["mpi4py.MPI"].COMM_WORLD
+            else:
+                from .mpi_facade.mpi4py import MPI
+
+                params["comm"] = MPI.COMM_WORLD
         super().__init__(params, level)
         if self.params.comm.size != self.coll.num_nodes:
             raise NotImplementedError(

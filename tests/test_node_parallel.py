@@ -244,3 +244,74 @@ def test_mpi_sweeper_equals_serial_sweeper_like_the_reference_test(tmp_path, kin
         cases = cases[::3] + cases[-2:]
     mp.spawn(_mpi_vs_serial_worker, args=(world, free_port(), kind, cases, REF_PATHS, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(tmp_path, f"ok_{r}")) for r in range(world))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ... and the reference's test ITSELF: pySDC/tests/test_sweepers/test_MPI_sweeper.py::individual_test(launch=False, ...)
+# called, unmodified, in every rank for the reference's own parameter grid (2 nodes x {GAUSS, RADAU-RIGHT} x {last_abs,
+# full_rel} x {imex, not} x {spread, copy, zero} x ML in {1, 2, 3}: 72 combinations; ML > 1 goes through the reference's
+# base_transfer_MPI), with the class names resolving to the plug-in classes (see tests/test_reference_suite.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stride):
+    import importlib
+    import itertools
+    import types
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    for p in reversed(ref_paths):
+        sys.path.insert(0, p)
+    import pysdc_b200.mpi_facade
+
+    sys.path.insert(0, pysdc_b200.mpi_facade.PATH)
+    transport = "gloo"
+    if kind == "cuda":
+        import torch
+
+        transport = "nccl" if torch.cuda.device_count() >= world else "gloo"
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+    dist.init_process_group(transport, rank=rank, world_size=world)
+    try:
+        from pysdc_b200 import backend
+        from pysdc_b200 import pysdc_plugin as plugin
+
+        if kind == "cuda":
+            backend.set_backend(backend.CudaBackend())
+        else:
+            from fake_backend import NumpyBackend
+
+            backend.set_backend(NumpyBackend())
+        base = "pySDC.implementations."
+        for name, exports in {
+                base + "problem_classes.HeatEquation_ND_FD": ["heatNd_unforced", "heatNd_forced"],
+                base + "sweeper_classes.generic_implicit": ["generic_implicit"],
+                base + "sweeper_classes.imex_1st_order": ["imex_1st_order"],
+                base + "sweeper_classes.generic_implicit_MPI": ["generic_implicit_MPI"],
+                base + "sweeper_classes.imex_1st_order_MPI": ["imex_1st_order_MPI"],
+                base + "transfer_classes.TransferMesh": ["mesh_to_mesh"]}.items():
+            mod = types.ModuleType(name)
+            for e in exports:
+                setattr(mod, e, getattr(plugin, e))
+            sys.modules[name] = mod
+        ref_test = importlib.import_module("pySDC.tests.test_sweepers.test_MPI_sweeper")
+        grid = list(itertools.product(["GAUSS", "RADAU-RIGHT"], ["last_abs", "full_rel"], [True, False],
+                                      ["spread", "copy", "zero"], [1, 2, 3]))
+        launches0 = backend.get_backend().launches
+        for quad_type, residual_type, imex, init_guess, ML in grid[::stride]:
+            ref_test.individual_test(launch=False, num_nodes=world, quad_type=quad_type, residual_type=residual_type,
+                                     imex=imex, init_guess=init_guess, useNCCL=False, ML=ML)
+        assert backend.get_backend().launches > launches0
+        with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
+            f.write(str(len(grid[::stride])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+@pytest.mark.parametrize("kind,stride", [("numpy", 1), pytest.param("cuda", 5, marks=pytest.mark.gpu)])
+def test_reference_test_MPI_sweeper_passes_on_plugin_classes(tmp_path, kind, stride):
+    world = 2  # test_MPI_sweeper.py:141 (num_nodes = 2)
+    mp.spawn(_reference_mpi_test_worker, args=(world, free_port(), kind, REF_PATHS, str(tmp_path), stride), nprocs=world,
+             join=True)
+    assert all(os.path.exists(os.path.join(tmp_path, f"ok_{r}")) for r in range(world))
