@@ -33,7 +33,7 @@ PARTS = ["__init__.py", "core", "helpers", "implementations",
          # runs them, unmodified, on the plug-in classes
          "tutorial", "tests/__init__.py", "tests/test_tutorials", "tests/test_transfer_classes/test_mesh_to_mesh.py",
          "tests/test_2d_fd_accuracy.py", "tests/test_convergence_controllers/test_check_convergence.py",
-         "tests/test_sweepers/test_MPI_sweeper.py"]
+         "tests/test_sweepers/test_MPI_sweeper.py", "tests/test_transfer_classes/test_base_transfer_MPI.py"]
 MANIFEST = os.path.join(DST, "MANIFEST.json")
 
 

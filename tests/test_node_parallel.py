@@ -252,7 +252,7 @@ def test_mpi_sweeper_equals_serial_sweeper_like_the_reference_test(tmp_path, kin
 # full_rel} x {imex, not} x {spread, copy, zero} x ML in {1, 2, 3}: 72 combinations; ML > 1 goes through the reference's
 # base_transfer_MPI), with the class names resolving to the plug-in classes (see tests/test_reference_suite.py)
 # ---------------------------------------------------------------------------------------------------------------------
-def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stride):
+def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stride, which="sweeper"):
     import importlib
     import itertools
     import types
@@ -294,6 +294,17 @@ def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stri
             for e in exports:
                 setattr(mod, e, getattr(plugin, e))
             sys.modules[name] = mod
+        if which == "base_transfer":
+            # pySDC/tests/test_transfer_classes/test_base_transfer_MPI.py:69-117: restrict / prolong / prolong_f of the
+            # reference's base_transfer_MPI (node-parallel levels) against its serial BaseTransfer, field by field
+            ref_test = importlib.import_module("pySDC.tests.test_transfer_classes.test_base_transfer_MPI")
+            launches0 = backend.get_backend().launches
+            for nvars in (32, 16):  # :46
+                ref_test._test_MPI_nonMPI_consistency(nvars)
+            assert backend.get_backend().launches > launches0
+            with open(os.path.join(out_dir, f"ok_{rank}"), "w") as f:
+                f.write("2")
+            return
         ref_test = importlib.import_module("pySDC.tests.test_sweepers.test_MPI_sweeper")
         grid = list(itertools.product(["GAUSS", "RADAU-RIGHT"], ["last_abs", "full_rel"], [True, False],
                                       ["spread", "copy", "zero"], [1, 2, 3]))
@@ -314,4 +325,12 @@ def test_reference_test_MPI_sweeper_passes_on_plugin_classes(tmp_path, kind, str
     world = 2  # test_MPI_sweeper.py:141 (num_nodes = 2)
     mp.spawn(_reference_mpi_test_worker, args=(world, free_port(), kind, REF_PATHS, str(tmp_path), stride), nprocs=world,
              join=True)
+    assert all(os.path.exists(os.path.join(tmp_path, f"ok_{r}")) for r in range(world))
+
+
+@pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
+@pytest.mark.parametrize("kind,world", [("numpy", 2), ("numpy", 3), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
+def test_reference_test_base_transfer_MPI_passes_on_plugin_classes(tmp_path, kind, world):
+    mp.spawn(_reference_mpi_test_worker, args=(world, free_port(), kind, REF_PATHS, str(tmp_path), 1, "base_transfer"),
+             nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(tmp_path, f"ok_{r}")) for r in range(world))
