@@ -261,9 +261,9 @@ class HeatMixin(_HostOperator, OutputMixin):
                                "'direct')")
         if solver_type == "GMRES" and (preconditioner is not None or comm is not None):
             raise ProblemError("solver_type='GMRES' runs without preconditioner and on one GPU")
-        # solver_type='direct' (the reference's default): a device factorisation exists for 1-D order-2 grids (tridiagonal
-        # Thomas solve); every other grid runs the CG down to its attainable accuracy instead (solve_system_batch)
-        self._direct_ok = ndim == 1 and order == 2
+        # solver_type='direct' (the reference's default): a device factorisation exists for 1-D order-2 grids of 3 .. 8192
+        # points (tridiagonal Thomas solve in shared memory); every other grid runs the CG down to its attainable accuracy instead (solve_system_batch)
+        self._direct_ok = ndim == 1 and order == 2 and 3 <= nvars[0] <= 8192  # (sdcb200_heat_direct_solve_1d's range)
 
         if preconditioner not in (None, "chebyshev"):
             raise ProblemError(f"unknown preconditioner {preconditioner!r} (have None, 'chebyshev')")

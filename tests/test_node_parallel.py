@@ -309,6 +309,8 @@ def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stri
         grid = list(itertools.product(["GAUSS", "RADAU-RIGHT"], ["last_abs", "full_rel"], [True, False],
                                       ["spread", "copy", "zero"], [1, 2, 3]))
         launches0 = backend.get_backend().launches
+        if kind == "cuda":  # the real kernels run the 512-point single-level cases; the 2- and 4-point grids of the
+            grid = [c for c in grid if c[4] == 1]  # reference's multi-level cases are covered on the numpy double
         for quad_type, residual_type, imex, init_guess, ML in grid[::stride]:
             ref_test.individual_test(launch=False, num_nodes=world, quad_type=quad_type, residual_type=residual_type,
                                      imex=imex, init_guess=init_guess, useNCCL=False, ML=ML)
@@ -320,7 +322,7 @@ def _reference_mpi_test_worker(rank, world, port, kind, ref_paths, out_dir, stri
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("kind,stride", [("numpy", 1), pytest.param("cuda", 5, marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("kind,stride", [("numpy", 1), pytest.param("cuda", 3, marks=pytest.mark.gpu)])
 def test_reference_test_MPI_sweeper_passes_on_plugin_classes(tmp_path, kind, stride):
     world = 2  # test_MPI_sweeper.py:141 (num_nodes = 2)
     mp.spawn(_reference_mpi_test_worker, args=(world, free_port(), kind, REF_PATHS, str(tmp_path), stride), nprocs=world,
