@@ -33,7 +33,9 @@ PARTS = ["__init__.py", "core", "helpers", "implementations",
          # runs them, unmodified, on the plug-in classes
          "tutorial", "tests/__init__.py", "tests/test_tutorials", "tests/test_transfer_classes/test_mesh_to_mesh.py",
          "tests/test_2d_fd_accuracy.py", "tests/test_convergence_controllers/test_check_convergence.py",
-         "tests/test_sweepers/test_MPI_sweeper.py", "tests/test_transfer_classes/test_base_transfer_MPI.py"]
+         "tests/test_sweepers/test_MPI_sweeper.py", "tests/test_transfer_classes/test_base_transfer_MPI.py",
+         # the reference's own CPU-vs-GPU check of its CuPy heat class (projects/GPU/heat.py:61-94)
+         "projects/__init__.py", "projects/GPU/__init__.py", "projects/GPU/heat.py"]
 MANIFEST = os.path.join(DST, "MANIFEST.json")
 
 

@@ -153,3 +153,43 @@ def test_reference_test_passes_on_plugin_classes(swapped_reference, module, func
     getattr(importlib.import_module(module), function)(**kwargs)
     # the test really went through the device classes (set-up-only tutorials launch nothing: u_exact is a host expression)
     assert backend.get_backend().launches > launches0 or (module, function) in SETUP_ONLY
+
+
+@pytest.mark.parametrize("kind", ["numpy", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_reference_cpu_vs_gpu_check_of_the_heat_class(kind, tmp_path, monkeypatch):
+    """pySDC/projects/GPU/heat.py::main, unmodified: the reference runs the same IMEX-SDC description (3-D periodic forced
+    heat, 32^3, CG) once with its CPU class and once with its GPU class (``HeatEquation_ND_FD_CuPy.heatNd_forced``) and
+    asserts ``abs(uend_gpu.get() - uend_cpu) < 1e-13`` (heat.py:94).  Here only the GPU class's module resolves to the
+    plug-in; the CPU class, the sweeper and the controller are the reference's."""
+    for p in reversed(REF_PATHS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from pysdc_b200 import backend
+
+    old_backend = backend._backend
+    if kind == "cuda":
+        backend.set_backend(backend.CudaBackend())
+    else:
+        from fake_backend import NumpyBackend
+
+        backend.set_backend(NumpyBackend())
+    from pysdc_b200 import pysdc_plugin as plugin
+
+    name = "pySDC.implementations.problem_classes.HeatEquation_ND_FD_CuPy"
+    saved = sys.modules.get(name)
+    mod = types.ModuleType(name)
+    mod.heatNd_forced, mod.heatNd_unforced = plugin.heatNd_forced, plugin.heatNd_unforced
+    sys.modules[name] = mod
+    sys.modules.pop("pySDC.projects.GPU.heat", None)
+    monkeypatch.chdir(tmp_path)
+    try:
+        launches0 = backend.get_backend().launches
+        importlib.import_module("pySDC.projects.GPU.heat").main()
+        assert backend.get_backend().launches > launches0
+    finally:
+        sys.modules.pop("pySDC.projects.GPU.heat", None)
+        if saved is None:
+            sys.modules.pop(name, None)
+        else:
+            sys.modules[name] = saved
+        backend.set_backend(old_backend)
