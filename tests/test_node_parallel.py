@@ -147,13 +147,13 @@ def test_node_parallel_sweepers_standalone(tmp_path, name, kind):
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("name,kind", _variants(CASES[2:], CASES[1:]))
+@pytest.mark.parametrize("name,kind", _variants(CASES[2:], CASES[2:]))
 def test_node_parallel_sweepers_under_the_reference_controller(tmp_path, name, kind):
     _check(tmp_path, name, kind, "plugin")
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("name,kind", _variants(CASES[1:2], CASES[:2]))
+@pytest.mark.parametrize("name,kind", _variants(CASES[1:2], CASES[:1]))
 def test_reference_node_parallel_sweepers_on_the_facade(tmp_path, name, kind):
     _check(tmp_path, name, kind, "reference")
 
@@ -231,7 +231,7 @@ def _mpi_vs_serial_worker(rank, world, port, kind, cases, ref_paths, out_dir):
 
 
 @pytest.mark.skipif(REF_PATHS is None, reason="reference tree not present (no /root/reference, no oracle/_ref)")
-@pytest.mark.parametrize("kind,world", [("numpy", 2), ("numpy", 3), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
+@pytest.mark.parametrize("kind,world", [("numpy", 3), pytest.param("cuda", 2, marks=pytest.mark.gpu)])
 def test_mpi_sweeper_equals_serial_sweeper_like_the_reference_test(tmp_path, kind, world):
     cases = []  # (quad_type, residual_type, imex, initial_guess, ML) as in test_MPI_sweeper.py:156-205
     for quad_type in ("GAUSS", "RADAU-RIGHT"):

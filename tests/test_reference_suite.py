@@ -12,8 +12,9 @@ collocation, hooks, statistics and the tutorials' own code stay the reference's.
 
 ``numpy`` variants: kernel library replaced by the numpy test double (CPU suite); ``cuda`` variants (``-m gpu``): the
 real CUDA kernels.  Not run: tutorial tests that need classes outside the path (Penning trap: step 3 B/C, 4 D), and the
-``mpirun`` launcher (6 C).  Step 5 C (advection, ``solver_type='direct'`` = GMRES to 1e-14 here) takes a minute on the numpy
-double and runs in the GPU suite only.
+``mpirun`` launcher (6 C).  Steps 5 B / C (PFASST; C: advection with ``solver_type='direct'`` = GMRES to 1e-14 here) take a
+minute each on the numpy double and run in the GPU suite only (2 s / 7 s there); tests/test_pysdc_dropin.py keeps a PFASST run
+under the reference's controller in the CPU suite.
 ``matplotlib`` is absent from the image; the tutorials only plot with it, so a do-nothing stand-in is installed."""
 import importlib
 import os
@@ -48,7 +49,8 @@ REFERENCE_TESTS = [
     ("pySDC.tests.test_tutorials.test_step_2", "test_C"), ("pySDC.tests.test_tutorials.test_step_3", "test_A"),
     ("pySDC.tests.test_tutorials.test_step_4", "test_A"), ("pySDC.tests.test_tutorials.test_step_4", "test_B"),
     ("pySDC.tests.test_tutorials.test_step_4", "test_C"), ("pySDC.tests.test_tutorials.test_step_5", "test_A"),
-    ("pySDC.tests.test_tutorials.test_step_5", "test_B"), ("pySDC.tests.test_tutorials.test_step_5", "test_C", {}, "gpu-only"),
+    ("pySDC.tests.test_tutorials.test_step_5", "test_B", {}, "gpu-only"),
+    ("pySDC.tests.test_tutorials.test_step_5", "test_C", {}, "gpu-only"),
     ("pySDC.tests.test_tutorials.test_step_6", "test_A"),
     ("pySDC.tests.test_tutorials.test_step_6", "test_B"),
     ("pySDC.tests.test_transfer_classes.test_mesh_to_mesh", "test_mesh_to_mesh_1d_dirichlet"),
@@ -59,9 +61,9 @@ REFERENCE_TESTS = [
     # (parametrised in the reference: the arguments are its own parameter lists; "gpu-only": thousands of CG iterations
     # per solve stand in for the 'direct' solver, which the numpy test double takes minutes for)
     ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=1)),
-    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=5)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=5), "gpu-only"),
     ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_iter", dict(maxiter=50), "gpu-only"),
-    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-3)),
+    ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-3), "gpu-only"),
     ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-5), "gpu-only"),
     ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_increment", dict(e_tol=1e-10), "gpu-only"),
     ("pySDC.tests.test_convergence_controllers.test_check_convergence", "test_convergence_by_residual", dict(restol=1e-3)),
