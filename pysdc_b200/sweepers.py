@@ -30,7 +30,6 @@ else holds a reference to such a field (the reference REBINDS ``L.u[m+1]`` to a 
 import sys
 
 import numpy as np
-import torch
 
 from .backend import get_backend
 from .errors import ParameterError
