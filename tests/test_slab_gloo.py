@@ -255,3 +255,77 @@ def test_nodes_times_slabs_matches_serial(tmp_path):
     finally:
         backend.set_backend(old)
         mesh.comm = old_comm
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# time slices x slabs: the time-parallel controller (one time slice per outer rank, uend -> u[0] hand-over between the
+# slices rank by rank of the space communicator) on slab-decomposed fields
+# ---------------------------------------------------------------------------------------------------------------------
+def _time_space_worker(rank, world, port, n, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SDCB200_CHECK_TAGS="1")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_backend import NumpyBackend
+        from pysdc_b200 import backend
+        from pysdc_b200.parallel import cartesian_comms
+        from pysdc_b200.pfasst import controller_MPI
+        from pysdc_b200.problems import heatNd_unforced
+        from pysdc_b200.stats import get_sorted
+        from pysdc_b200.sweepers import generic_implicit
+
+        backend.set_backend(NumpyBackend())
+        time_comm, space_comm = cartesian_comms(2, world // 2)
+        sp = _spec(n)
+        c = controller_MPI({"logger_level": 40}, dict(
+            problem_class=heatNd_unforced, problem_params=dict(sp["problem_params"], comm=space_comm),
+            sweeper_class=generic_implicit, sweeper_params=dict(sp["sweeper_params"], QI="LU"),
+            level_params=sp["level_params"], step_params=sp["step_params"]), comm=time_comm)
+        P = c.S.levels[0].prob
+        u0 = P.dtype_u(P.init)
+        u0[:] = np.random.default_rng(1234).standard_normal((n, n, n))
+        uend, stats = c.run(u0=u0, t0=0.0, Tend=4e-3)  # two blocks of two slices
+        np.save(os.path.join(out_dir, f"uend_{rank}.npy"), uend.gather())
+        np.save(os.path.join(out_dir, f"times_{rank}.npy"), np.array([t for t, _ in get_sorted(stats, type="niter", sortby="time")]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_slices_times_slabs_matches_serial_time_stepping(tmp_path):
+    from conftest import free_port
+
+    n, world = 13, 4
+    mp.spawn(_time_space_worker, args=(world, free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_backend import NumpyBackend
+    from pysdc_b200 import backend
+    from pysdc_b200.controller import controller_nonMPI
+    from pysdc_b200.datatypes import mesh
+    from pysdc_b200.problems import heatNd_unforced
+    from pysdc_b200.sweepers import generic_implicit
+
+    old, old_comm = backend._backend, mesh.comm
+    backend.set_backend(NumpyBackend())
+    try:
+        mesh.comm = None
+        sp = _spec(n)
+        c = controller_nonMPI(1, {"logger_level": 40}, dict(
+            problem_class=heatNd_unforced, problem_params=sp["problem_params"], sweeper_class=generic_implicit,
+            sweeper_params=dict(sp["sweeper_params"], QI="LU"), level_params=sp["level_params"],
+            step_params=sp["step_params"]))
+        P = c.MS[0].levels[0].prob
+        u0 = P.dtype_u(P.init)
+        u0[:] = np.random.default_rng(1234).standard_normal((n, n, n))
+        ref = c.run(u0=u0, t0=0.0, Tend=4e-3)[0].get()
+        got = [np.load(os.path.join(tmp_path, f"uend_{r}.npy")) for r in range(world)]
+        for r in range(world):
+            assert np.array_equal(got[r], got[0])  # block-end broadcast: the same end value on every rank
+            # time-parallel SDC iterates every step to restol = 1e-9: the end values agree to that level, not to rounding
+            assert np.max(np.abs(got[r] - ref)) / np.max(np.abs(ref)) < 1e-8
+        # slice 0 (ranks 0, 1) took steps 0 and 2, slice 1 (ranks 2, 3) steps 1 and 3
+        assert np.allclose(np.load(os.path.join(tmp_path, "times_0.npy")), [0.0, 2e-3])
+        assert np.allclose(np.load(os.path.join(tmp_path, "times_3.npy")), [1e-3, 3e-3])
+    finally:
+        backend.set_backend(old)
+        mesh.comm = old_comm
